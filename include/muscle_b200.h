@@ -1,0 +1,164 @@
+/* muscle_b200.h -- C ABI of libmuscle_b200.so, the B200-native pair engine for MUSCLE5's MPCFlat stage.
+ *
+ * The reference (rcedgar/muscle @ 6c69a9b) has no plugin/FFI interface for this path: it is C++
+ * free functions and the MPCFlat / PProg classes linked into one binary.  The boundary below is
+ * therefore defined by the reference's call sites; every entry point names
+ * the reference code it replaces (paths relative to /root/reference/src).  All functions are
+ * extern "C", take plain pointers and sizes, return 0 on success or a negative MB200_E* code, and
+ * leave a message retrievable with mb200_last_error() (the reference convention is Die() ->
+ * exit(1), myutils.cpp:883; the C++ shim in INTEGRATION.md turns a non-zero return into Die()).
+ *
+ * Ownership: the library owns all device memory inside the context; every host buffer is
+ * caller-allocated and never freed by the library.  A context is bound to one CUDA device and may
+ * be used by one host thread at a time (the reference's OpenMP pair loops collapse into one batch
+ * call issued by one thread; use one context per thread for UClust-style per-pair calls).
+ *
+ * There is NO CPU fallback: without a CUDA device every compute entry point fails with
+ * MB200_ENODEV.
+ */
+#ifndef MUSCLE_B200_H
+#define MUSCLE_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MB200_OK         0
+#define MB200_EINVAL    -1   /* bad argument / call order                                  */
+#define MB200_ENODEV    -2   /* no usable CUDA device                                      */
+#define MB200_ECUDA     -3   /* CUDA runtime error (message has the cudaError string)      */
+#define MB200_ENOMEM    -4   /* device allocation failed                                   */
+#define MB200_EOVERFLOW -5   /* reference guard LX*LY*5+100 > INT_MAX (fwdflat3.cpp:17) or
+                                more than MB200_MAX_ROW_NNZ candidate entries in one row   */
+#define MB200_EALPHABET -6   /* more distinct residue classes than the device tables hold  */
+
+#define MB200_MAX_ROW_NNZ 128  /* a posterior row holds <= 100 entries >= 0.01 (they sum to <= 1) */
+
+typedef struct mb200_ctx mb200_ctx;
+
+/* Sparse wire format = MySparseMx's own (mysparsemx.h:6-98): uint32 offsets[LX+1] and
+ * nnz x {float P; uint32 col}, columns ascending, so host MySparseMx objects are filled by memcpy. */
+typedef struct { float p; uint32_t col; } mb200_entry;
+
+/* ---- lifetime ---------------------------------------------------------------------------- */
+int         mb200_create(int device, mb200_ctx **out);
+void        mb200_destroy(mb200_ctx *ctx);
+const char *mb200_last_error(const mb200_ctx *ctx);   /* ctx may be NULL: last create() error */
+/* library/ABI version and the sm target it was compiled for, e.g. "0.1.0 sm_100a" */
+const char *mb200_version(void);
+
+/* ---- inputs ------------------------------------------------------------------------------ */
+/* Upload the PairHMM tables exactly as the host computed them: PairHMM::m_StartScore[5],
+ * m_TransScore[5][5], m_InsScore[256], m_MatchScore[256][256] (pairhmm.h:26-29, filled by
+ * HMMParams::ToPairHMM hmmparams.cpp:298-409), plus MIN_SPARSE_SCORE = logf(0.01f) as evaluated
+ * by the host libm (mysparsemx.h:4).  Call again after every ToPairHMM (e.g. -perturb replicates). */
+int mb200_set_hmm(mb200_ctx *ctx, const float start[5], const float trans[25],
+                  const float ins[256], const float match[65536], float min_sparse_score);
+
+/* Upload the sequences (raw bytes exactly as Sequence::GetBytePtr returns them, sequence.h:56-61).
+ * offsets[nseq+1] index into bytes.  Replaces the label->sequence registry lookups of
+ * CalcPost (calcpost.cpp:4-36, globalinputms.cpp:125-143): the library speaks indices.
+ * Invalidates any stored posteriors. */
+int mb200_set_seqs(mb200_ctx *ctx, uint32_t nseq, const uint8_t *bytes, const uint64_t *offsets);
+
+/* ---- posterior stage --------------------------------------------------------------------- */
+/* Replaces the OpenMP loop MPCFlat::CalcPosteriors (mpcflat.cpp:214-252) and, per pair,
+ * MPCFlat::CalcPosterior (calcposteriorflat.cpp:45-92) = CalcPost (calcpost.cpp:4: CalcFwdFlat
+ * fwdflat3.cpp:12, CalcBwdFlat bwdflat3.cpp:10, CalcPostFlat calcposteriorflat.cpp:4,
+ * CalcTotalProbFlat totalprobflat.cpp:3) + MySparseMx::FromPost (mysparsemx.cpp:115) +
+ * CalcAlnScoreFlat (calcalnscoreflat.cpp:4) + EA = Score/min(LX,LY).
+ * Pair k is (pair_x[k], pair_y[k]); X indexes rows.  The sparse posteriors stay resident on the
+ * device as "the store" (replacing m_SparsePosts1, mpcflat.h:46-49); ea_out[k] (host, may be
+ * NULL) receives what the reference writes to m_DistMx[x][y].
+ * Also serves PProg::GetPostPairsAlignedFlat (getpostpairsalignedflat.cpp:5), CalcEADistMx
+ * (eadistmx.cpp:7) and AlignPairFlat_SparsePost (alignpairflat.cpp:3) with their pair lists. */
+#define MB200_POST_DEFAULT 0u
+int mb200_posteriors(mb200_ctx *ctx, uint32_t npairs, const uint32_t *pair_x, const uint32_t *pair_y,
+                     uint32_t flags, float *ea_out);
+
+/* Same, all-pairs convenience: pairs (i<j) in the reference's row-major order
+ * (MPCFlat::InitPairs mpcflat.cpp:139-159), restricted to pair indexes [p_lo,p_hi) so that a
+ * multi-GPU caller can shard; ea_out has p_hi-p_lo slots.  Store pair k <-> global pair p_lo+k. */
+int mb200_posteriors_allpairs(mb200_ctx *ctx, uint32_t p_lo, uint32_t p_hi, float *ea_out);
+
+/* Store introspection (host copies).  nnz_out[npairs]. */
+int mb200_store_npairs(const mb200_ctx *ctx, uint32_t *npairs);
+int mb200_store_nnz(mb200_ctx *ctx, uint32_t *nnz_out, uint64_t *total_nnz);
+/* Copy one stored pair out in MySparseMx layout: offsets[LX+1], entries[nnz] (host buffers).
+ * Replaces reading (*m_ptrSparsePosts)[PairIndex] (mpcflat.cpp:88-98). */
+int mb200_export_pair(mb200_ctx *ctx, uint32_t pair, uint32_t *offsets, mb200_entry *entries);
+/* Copy every stored pair out, packed back to back in store order: offsets_concat has
+ * sum(LX_k+1) slots (each pair's offsets start at 0), entries_concat has total_nnz slots. */
+int mb200_export_all(mb200_ctx *ctx, uint32_t *offsets_concat, mb200_entry *entries_concat);
+
+/* ---- store exchange (multi-GPU) ------------------------------------- */
+/* Device-side packed image of the store for NCCL all-gather: row offsets and entries of every
+ * stored pair, in store order.  The pointers are device pointers owned by the context and stay
+ * valid until the store changes.  n_offsets = sum(LX_k+1), n_entries = total nnz. */
+int mb200_store_pack(mb200_ctx *ctx, const uint32_t **d_offsets, uint64_t *n_offsets,
+                     const mb200_entry **d_entries, uint64_t *n_entries);
+/* Replace the store with the concatenation of packed images of the all-pairs ranges
+ * [p_lo,p_hi) (the gathered result); d_* are device pointers (caller-owned, copied). */
+int mb200_store_load_allpairs(mb200_ctx *ctx, uint32_t p_lo, uint32_t p_hi,
+                              const uint32_t *d_offsets, uint64_t n_offsets,
+                              const mb200_entry *d_entries, uint64_t n_entries);
+/* values-only image (float per entry, store order) for the exchange between consistency
+ * iterations: the pattern is invariant (mysparsemx.cpp:87-113). */
+int mb200_store_values(mb200_ctx *ctx, float *d_values_out, uint64_t n_entries);
+int mb200_store_set_values(mb200_ctx *ctx, const float *d_values, uint64_t first_entry, uint64_t n_entries);
+
+/* ---- consistency (relax) ------------------------------------------------------------------ */
+/* One Jacobi iteration over the all-pairs store: replaces MPCFlat::ConsIter (consflat.cpp:5-23)
+ * = for every pair MPCFlat::ConsPair (conspairflat.cpp:10-110) with RelaxFlat_ZX_ZY / _XZ_ZY /
+ * _XZ_YZ (relaxflat.cpp:4,33,62) and MySparseMx::UpdateFromPost (mysparsemx.cpp:87), followed by
+ * the buffer swap.  Requires the store to hold all N(N-1)/2 pairs of the current sequences.
+ * Only pairs with index in [p_lo,p_hi) are updated (multi-GPU sharding; pass 0,npairs for all);
+ * the others keep their old values until mb200_store_set_values brings the peers' results. */
+int mb200_consistency_iter(mb200_ctx *ctx, uint32_t p_lo, uint32_t p_hi);
+
+/* ---- posterior decoding ------------------------------------------------------------------- */
+/* Batched CalcAlnFlat (calcalnflat.cpp:6-46) + TraceBackFlat (tracebackflat.cpp:3-37) on the
+ * stored pairs: for each listed store pair, densify its sparse posterior, run the max-sum DP with
+ * Best3 tie order (best3.h:5-28) and trace back.  paths_out: concatenated, pair k's path starts
+ * at path_off[k] (path_off[k] = sum_{m<k}(LX_m+LY_m+1)), NUL terminated, letters B/X/Y;
+ * scores_out[k] = DP score.  Serves AlignPairFlat (alignpairflat.cpp:23) and
+ * PProg::GetPostPairsAlignedFlat (getpostpairsalignedflat.cpp:62-90). */
+int mb200_align_pairs(mb200_ctx *ctx, uint32_t n, const uint32_t *store_pairs,
+                      char *paths_out, const uint64_t *path_off, float *scores_out);
+
+/* MPCFlat::AlignAlns (alnalnsflat.cpp:7-52) minus the gap insertion: BuildPost
+ * (buildpostflat.cpp:18-105) of two groups of already-aligned sequences followed by CalcAlnFlat +
+ * traceback.  ids_a[na]/ids_b[nb]: sequence indexes; pos2col_*: concatenated position->column maps
+ * (Sequence::GetPosToCol sequence.cpp:144-154), sequence s of group a starting at
+ * sum of lengths of the previous group members; cols_a/cols_b: column counts.
+ * path_out needs cols_a+cols_b+1 bytes; post_out (cols_a*cols_b floats, host) may be NULL. */
+int mb200_align_groups(mb200_ctx *ctx,
+                       uint32_t na, const uint32_t *ids_a, const uint32_t *pos2col_a, uint32_t cols_a,
+                       uint32_t nb, const uint32_t *ids_b, const uint32_t *pos2col_b, uint32_t cols_b,
+                       char *path_out, float *score_out, float *post_out);
+
+/* ---- per-pair debug/parity surface -------------------------------------------------------- */
+/* CalcPost (calcpost.cpp:4-36) for one pair with the dense result copied to the host:
+ * post_out[LX*LY] thresholded posterior (CalcPostFlat), fwd_m_out / bwd_m_out (may be NULL)
+ * the M-state planes [(LX)*(LY)] for rows/cols 1.., total_out the log total probability. */
+int mb200_calc_post_dense(mb200_ctx *ctx, uint32_t x, uint32_t y, float *post_out,
+                          float *fwd_m_out, float *bwd_m_out, float *total_out);
+
+/* ---- instrumentation ---------------------------------------------------------------------- */
+typedef struct
+	{
+	uint64_t kernel_launches;    /* kernels launched by this context since creation         */
+	uint64_t cells;              /* DP cells of the last posterior call                     */
+	float    last_kernel_ms;     /* device time of the dominant kernel(s) of the last call  */
+	float    last_total_ms;      /* device time of the whole last call (events)             */
+	uint64_t h2d_bytes;          /* host->device bytes moved by the last call               */
+	uint64_t d2h_bytes;          /* device->host bytes moved by the last call               */
+	} mb200_stats;
+int mb200_get_stats(const mb200_ctx *ctx, mb200_stats *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,625 @@
+// engine.cu -- host side of libmuscle_b200.so: context, uploads, work binning, launches, C ABI.
+//
+// The C ABI (include/muscle_b200.h) mirrors the reference's MPCFlat call sites; nothing here
+// falls back to the CPU: without a CUDA device every entry point fails with MB200_ENODEV.
+#include "engine.h"
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <numeric>
+
+static char g_create_error[512] = "";
+
+int mb_fail(mb200_ctx *ctx, int code, const char *fmt, ...)
+	{
+	char *dst = ctx ? ctx->err : g_create_error;
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(dst, 512, fmt, ap);
+	va_end(ap);
+	return code;
+	}
+
+#define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) \
+	return mb_fail(ctx, e_ == cudaErrorMemoryAllocation ? MB200_ENOMEM : MB200_ECUDA, \
+	  "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); } while (0)
+
+int DevBuf::ensure(size_t need)
+	{
+	if (need <= cap)
+		return 0;
+	if (p)
+		cudaFree(p);
+	p = nullptr;
+	cap = 0;
+	size_t want = need + need/8 + 256;
+	cudaError_t e = cudaMalloc(&p, want);
+	if (e != cudaSuccess)
+		{
+		want = need;
+		e = cudaMalloc(&p, want);
+		}
+	if (e != cudaSuccess)
+		{
+		cudaGetLastError();
+		return -1;
+		}
+	cap = want;
+	return 0;
+	}
+
+void DevBuf::release()
+	{
+	if (p)
+		cudaFree(p);
+	p = nullptr;
+	cap = 0;
+	}
+
+#define ENSURE(buf, bytes) do { if ((buf).ensure(bytes) != 0) \
+	return mb_fail(ctx, MB200_ENOMEM, "device allocation of %zu bytes failed (%s)", (size_t)(bytes), #buf); } while (0)
+
+extern "C" {
+
+const char *mb200_version(void) { return "0.1.0 sm_100a"; }
+
+const char *mb200_last_error(const mb200_ctx *ctx) { return ctx ? ctx->err : g_create_error; }
+
+int mb200_create(int device, mb200_ctx **out)
+	{
+	mb200_ctx *ctx = nullptr;
+	if (out == nullptr)
+		return mb_fail(nullptr, MB200_EINVAL, "mb200_create: out is NULL");
+	*out = nullptr;
+	int ndev = 0;
+	cudaError_t e = cudaGetDeviceCount(&ndev);
+	if (e != cudaSuccess || ndev == 0)
+		{
+		cudaGetLastError();
+		return mb_fail(nullptr, MB200_ENODEV, "no CUDA device (%s); libmuscle_b200 has no CPU path",
+		  e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+		}
+	if (device < 0 || device >= ndev)
+		return mb_fail(nullptr, MB200_EINVAL, "device %d out of range (have %d)", device, ndev);
+	ctx = new mb200_ctx();
+	ctx->device = device;
+	ctx->err[0] = 0;
+	if (cudaSetDevice(device) != cudaSuccess || cudaGetDeviceProperties(&ctx->prop, device) != cudaSuccess)
+		{
+		mb_fail(nullptr, MB200_ECUDA, "cudaSetDevice(%d) failed: %s", device, cudaGetErrorString(cudaGetLastError()));
+		delete ctx;
+		return MB200_ECUDA;
+		}
+	cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+	cudaEventCreate(&ctx->ev0);
+	cudaEventCreate(&ctx->ev1);
+	cudaEventCreate(&ctx->ev2);
+	cudaEventCreate(&ctx->ev3);
+	*out = ctx;
+	return MB200_OK;
+	}
+
+void mb200_destroy(mb200_ctx *ctx)
+	{
+	if (!ctx)
+		return;
+	cudaSetDevice(ctx->device);
+	cudaStreamSynchronize(ctx->stream);
+	DevBuf *bufs[] = { &ctx->d_matchT, &ctx->d_insT, &ctx->d_codes, &ctx->d_seqoff, &ctx->d_seqlen, &ctx->d_px,
+	  &ctx->d_py, &ctx->d_order, &ctx->d_counters, &ctx->d_fm, &ctx->d_edge, &ctx->d_rows, &ctx->d_rowcnt,
+	  &ctx->d_rowoff, &ctx->d_rowbase, &ctx->d_entries, &ctx->d_cursor, &ctx->d_entbase, &ctx->d_nnz,
+	  &ctx->d_ea, &ctx->d_err, &ctx->d_dbg, &ctx->d_pack_off, &ctx->d_pack_ent, &ctx->d_entries2,
+	  &ctx->d_tr_rowoff, &ctx->d_tr_rowbase, &ctx->d_tr_entries, &ctx->d_tr_entbase, &ctx->d_tr_perm,
+	  &ctx->d_tmp, &ctx->d_tmp2 };
+	for (DevBuf *b : bufs)
+		b->release();
+	cudaEventDestroy(ctx->ev0);
+	cudaEventDestroy(ctx->ev1);
+	cudaEventDestroy(ctx->ev2);
+	cudaEventDestroy(ctx->ev3);
+	cudaStreamDestroy(ctx->stream);
+	delete ctx;
+	}
+
+int mb200_get_stats(const mb200_ctx *ctx, mb200_stats *out)
+	{
+	if (!ctx || !out)
+		return MB200_EINVAL;
+	*out = ctx->stats;
+	return MB200_OK;
+	}
+
+// ------------------------------------------------------------------------------------------
+// HMM tables: bytes with identical insert score and identical match row/column are merged into
+// one residue class so that the device tables stay tiny (21 classes for proteins).
+static int recode_seqs(mb200_ctx *ctx);
+
+int mb200_set_hmm(mb200_ctx *ctx, const float start[5], const float trans[25], const float ins[256],
+  const float match[65536], float min_sparse_score)
+	{
+	if (!ctx || !start || !trans || !ins || !match)
+		return mb_fail(ctx, MB200_EINVAL, "mb200_set_hmm: NULL argument");
+	cudaSetDevice(ctx->device);
+	MbHmm &h = ctx->hmm;
+	// state order M=0, IX=1, IY=2, JX=3, JY=4 (pairhmm.h:11-19); aliases of hmmscores.h:1-13
+	h.tSM = start[0]; h.tSI = start[1]; h.tSJ = start[3];
+	h.tMM = trans[0*5 + 0]; h.tMI = trans[0*5 + 1]; h.tMJ = trans[0*5 + 3];
+	h.tII = trans[1*5 + 1]; h.tIM = trans[1*5 + 0];
+	h.tJJ = trans[3*5 + 3]; h.tJM = trans[3*5 + 0];
+	h.minScore = min_sparse_score;
+
+	// class of byte b = first byte a<=b with the same insert score and the same match row & column
+	int nclass = 0;
+	int rep[256];
+	for (int b = 0; b < 256; ++b)
+		{
+		int found = -1;
+		for (int k = 0; k < nclass && found < 0; ++k)
+			{
+			const int a = rep[k];
+			if (memcmp(&ins[a], &ins[b], sizeof(float)) != 0)
+				continue;
+			if (memcmp(match + 256*a, match + 256*b, 256*sizeof(float)) != 0)
+				continue;
+			bool same = true;
+			for (int r = 0; r < 256 && same; ++r)
+				same = memcmp(&match[256*r + a], &match[256*r + b], sizeof(float)) == 0;
+			if (same)
+				found = k;
+			}
+		if (found < 0)
+			{
+			if (nclass >= 256)
+				return mb_fail(ctx, MB200_EALPHABET, "internal: class table overflow");
+			rep[nclass] = b;
+			found = nclass++;
+			}
+		ctx->byte2class[b] = (uint8_t) found;
+		}
+	if (nclass > MB_MAX_K)
+		return mb_fail(ctx, MB200_EALPHABET, "%d distinct residue classes in the HMM tables, device tables hold %d",
+		  nclass, MB_MAX_K);
+	h.K = nclass;
+	h.KS = nclass | 1;                 // odd row stride spreads match rows over the smem banks
+	h.pad = ctx->byte2class[0];       // the reference reads byte 0 past the sequence end (bwdflat3.cpp:48,66)
+	std::vector<float> insT(h.K), matchT((size_t) h.K*h.KS, 0.0f);
+	for (int a = 0; a < h.K; ++a)
+		{
+		insT[a] = ins[rep[a]];
+		for (int b = 0; b < h.K; ++b)
+			matchT[(size_t) a*h.KS + b] = match[256*rep[a] + rep[b]];
+		}
+	ENSURE(ctx->d_insT, insT.size()*sizeof(float));
+	ENSURE(ctx->d_matchT, matchT.size()*sizeof(float));
+	CU(cudaMemcpyAsync(ctx->d_insT.p, insT.data(), insT.size()*sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+	CU(cudaMemcpyAsync(ctx->d_matchT.p, matchT.data(), matchT.size()*sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+	CU(cudaStreamSynchronize(ctx->stream));
+	ctx->have_hmm = true;
+	ctx->store_valid = false;
+	if (ctx->nseq > 0)
+		return recode_seqs(ctx);
+	return MB200_OK;
+	}
+
+static int recode_seqs(mb200_ctx *ctx)
+	{
+	std::vector<uint8_t> codes(ctx->h_bytes.size());
+	for (size_t k = 0; k < codes.size(); ++k)
+		codes[k] = ctx->byte2class[ctx->h_bytes[k]];
+	ENSURE(ctx->d_codes, codes.size() + 16);
+	CU(cudaMemcpyAsync(ctx->d_codes.p, codes.data(), codes.size(), cudaMemcpyHostToDevice, ctx->stream));
+	CU(cudaStreamSynchronize(ctx->stream));
+	ctx->stats.h2d_bytes += codes.size();
+	return MB200_OK;
+	}
+
+int mb200_set_seqs(mb200_ctx *ctx, uint32_t nseq, const uint8_t *bytes, const uint64_t *offsets)
+	{
+	if (!ctx || !bytes || !offsets || nseq == 0)
+		return mb_fail(ctx, MB200_EINVAL, "mb200_set_seqs: bad argument");
+	cudaSetDevice(ctx->device);
+	ctx->nseq = nseq;
+	ctx->h_off.assign(offsets, offsets + nseq + 1);
+	ctx->h_len.resize(nseq);
+	for (uint32_t i = 0; i < nseq; ++i)
+		{
+		if (offsets[i + 1] <= offsets[i])
+			return mb_fail(ctx, MB200_EINVAL, "sequence %u is empty or offsets not increasing", i);
+		const uint64_t L = offsets[i + 1] - offsets[i];
+		if (L > 0x7fffffffull)
+			return mb_fail(ctx, MB200_EOVERFLOW, "sequence %u too long", i);
+		ctx->h_len[i] = (uint32_t) L;
+		}
+	ctx->h_bytes.assign(bytes + offsets[0], bytes + offsets[nseq]);
+	const uint64_t o0 = offsets[0];
+	for (auto &o : ctx->h_off)
+		o -= o0;
+	ENSURE(ctx->d_seqoff, (nseq + 1)*sizeof(uint64_t));
+	ENSURE(ctx->d_seqlen, nseq*sizeof(uint32_t));
+	CU(cudaMemcpyAsync(ctx->d_seqoff.p, ctx->h_off.data(), (nseq + 1)*sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+	CU(cudaMemcpyAsync(ctx->d_seqlen.p, ctx->h_len.data(), nseq*sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+	ctx->stats.h2d_bytes = (nseq + 1)*sizeof(uint64_t) + nseq*sizeof(uint32_t);
+	ctx->store_valid = false;
+	ctx->store_allpairs = false;
+	if (ctx->have_hmm)
+		return recode_seqs(ctx);
+	CU(cudaStreamSynchronize(ctx->stream));
+	return MB200_OK;
+	}
+
+// ------------------------------------------------------------------------------------------
+// posterior stage
+static int run_posteriors(mb200_ctx *ctx, float *ea_out, const PostDebug *dbg, int force_c)
+	{
+	const uint32_t np = (uint32_t) ctx->h_px.size();
+	if (!ctx->have_hmm || ctx->nseq == 0)
+		return mb_fail(ctx, MB200_EINVAL, "mb200_posteriors: call mb200_set_hmm and mb200_set_seqs first");
+	cudaSetDevice(ctx->device);
+	cudaStream_t st = ctx->stream;
+	ctx->stats.h2d_bytes = 0;
+	ctx->stats.d2h_bytes = 0;
+	CU(cudaEventRecord(ctx->ev0, st));
+
+	// per-pair geometry, reference overflow guard (fwdflat3.cpp:17-18)
+	std::vector<uint64_t> rowbase(np + 1);
+	uint64_t cells = 0, rows_total = 0, est_entries = 0;
+	for (uint32_t k = 0; k < np; ++k)
+		{
+		const uint32_t x = ctx->h_px[k], y = ctx->h_py[k];
+		if (x >= ctx->nseq || y >= ctx->nseq)
+			return mb_fail(ctx, MB200_EINVAL, "pair %u references sequence out of range", k);
+		const double LX = ctx->h_len[x], LY = ctx->h_len[y];
+		if (LX*LY*5 + 100 > 2147483647.0)
+			return mb_fail(ctx, MB200_EOVERFLOW, "HMM overflow, sequence lengths %u, %u (max ~21k)",
+			  ctx->h_len[x], ctx->h_len[y]);
+		rowbase[k] = rows_total;
+		rows_total += ctx->h_len[x] + 1;
+		cells += (uint64_t) ctx->h_len[x]*ctx->h_len[y];
+		est_entries += (uint64_t) ctx->h_len[x]*ctx->nnz_per_row_cap;
+		}
+	rowbase[np] = rows_total;
+	ctx->h_rowbase = rowbase;
+	ctx->stats.cells = cells;
+
+	ENSURE(ctx->d_px, np*sizeof(uint32_t));
+	ENSURE(ctx->d_py, np*sizeof(uint32_t));
+	ENSURE(ctx->d_rowbase, (np + 1)*sizeof(uint64_t));
+	ENSURE(ctx->d_rowoff, rows_total*sizeof(uint32_t));
+	ENSURE(ctx->d_entbase, np*sizeof(uint64_t));
+	ENSURE(ctx->d_nnz, np*sizeof(uint32_t));
+	ENSURE(ctx->d_ea, np*sizeof(float));
+	ENSURE(ctx->d_order, np*sizeof(uint32_t));
+	ENSURE(ctx->d_counters, (MB_MAX_C + 1)*sizeof(uint32_t));
+	ENSURE(ctx->d_cursor, sizeof(unsigned long long));
+	ENSURE(ctx->d_err, sizeof(int));
+	CU(cudaMemcpyAsync(ctx->d_px.p, ctx->h_px.data(), np*sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+	CU(cudaMemcpyAsync(ctx->d_py.p, ctx->h_py.data(), np*sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+	CU(cudaMemcpyAsync(ctx->d_rowbase.p, rowbase.data(), (np + 1)*sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+	ctx->stats.h2d_bytes += 2ull*np*sizeof(uint32_t) + (np + 1)*sizeof(uint64_t);
+
+	// bin pairs by C = columns per lane; inside a bin longest X first
+	std::vector<std::vector<uint32_t>> bins(MB_MAX_C + 1);
+	for (uint32_t k = 0; k < np; ++k)
+		{
+		const uint32_t LY = ctx->h_len[ctx->h_py[k]];
+		int C = force_c > 0 ? force_c : (int) std::min<uint32_t>(MB_MAX_C, (LY + 31)/32);
+		bins[C].push_back(k);
+		}
+	std::vector<uint32_t> order;
+	order.reserve(np);
+	std::vector<uint32_t> bin_start(MB_MAX_C + 2, 0);
+	for (int C = 1; C <= MB_MAX_C; ++C)
+		{
+		auto &b = bins[C];
+		std::stable_sort(b.begin(), b.end(), [&](uint32_t a, uint32_t c2)
+			{
+			const uint64_t ca = (uint64_t) ctx->h_len[ctx->h_px[a]]*ctx->h_len[ctx->h_py[a]];
+			const uint64_t cb = (uint64_t) ctx->h_len[ctx->h_px[c2]]*ctx->h_len[ctx->h_py[c2]];
+			return ca > cb;
+			});
+		bin_start[C] = (uint32_t) order.size();
+		order.insert(order.end(), b.begin(), b.end());
+		}
+	bin_start[MB_MAX_C + 1] = (uint32_t) order.size();
+	CU(cudaMemcpyAsync(ctx->d_order.p, order.data(), np*sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+	ctx->stats.h2d_bytes += np*sizeof(uint32_t);
+	CU(cudaMemsetAsync(ctx->d_counters.p, 0, (MB_MAX_C + 1)*sizeof(uint32_t), st));
+	CU(cudaMemsetAsync(ctx->d_err.p, 0, sizeof(int), st));
+
+	for (int attempt = 0; attempt < 3; ++attempt)
+		{
+		ENSURE(ctx->d_entries, (est_entries + 64)*sizeof(mb200_entry));
+		CU(cudaMemsetAsync(ctx->d_cursor.p, 0, sizeof(unsigned long long), st));
+		CU(cudaMemsetAsync(ctx->d_counters.p, 0, (MB_MAX_C + 1)*sizeof(uint32_t), st));
+		CU(cudaMemsetAsync(ctx->d_err.p, 0, sizeof(int), st));
+		CU(cudaEventRecord(ctx->ev1, st));
+		for (int C = 1; C <= MB_MAX_C; ++C)
+			{
+			const auto &b = bins[C];
+			if (b.empty())
+				continue;
+			uint32_t lxmax = 0, lymax = 0;
+			for (uint32_t k : b)
+				{
+				lxmax = std::max(lxmax, ctx->h_len[ctx->h_px[k]]);
+				lymax = std::max(lymax, ctx->h_len[ctx->h_py[k]]);
+				}
+			const uint32_t W = 32u*C;
+			const uint32_t nstrips = (lymax + W - 1)/W;
+			int smem_static = 0, occ = 0;
+			mb_post_dispatch(C, 2, dim3(), 0, st, nullptr, &smem_static);
+			const size_t smem = (size_t) smem_static + (size_t) ctx->hmm.K*ctx->hmm.KS*sizeof(float);
+			mb_post_dispatch(C, 1, dim3(), smem, st, nullptr, &occ);
+			if (occ <= 0)
+				return mb_fail(ctx, MB200_ECUDA, "k_posterior<%d> cannot be resident (smem %zu)", C, smem);
+			uint32_t nblocks = (uint32_t) occ*ctx->prop.multiProcessorCount;
+			const uint32_t need_blocks = ((uint32_t) b.size() + MB_WARPS_PER_BLOCK - 1)/MB_WARPS_PER_BLOCK;
+			nblocks = std::max(1u, std::min(nblocks, need_blocks));
+			const size_t nwarps = (size_t) nblocks*MB_WARPS_PER_BLOCK;
+			// scratch geometry; shrink the resident warp count if the Forward-M spill would not fit
+			PostParams P;
+			memset(&P, 0, sizeof P);
+			P.lxmax = lxmax;
+			P.fm_rows = lxmax + 33;
+			P.fm_stride = (size_t) nstrips*P.fm_rows*W;
+			P.edge_stride = 2*((size_t) lxmax + 2);
+			P.rows_stride = (size_t) lxmax*MB_CAP;
+			P.rowcnt_stride = ((size_t) lxmax + 31)/16*16;
+			size_t per_warp = P.fm_stride*4 + P.edge_stride*16 + P.rows_stride*8 + P.rowcnt_stride;
+			size_t free_b = 0, total_b = 0;
+			cudaMemGetInfo(&free_b, &total_b);
+			const size_t have = free_b + ctx->d_fm.cap + ctx->d_edge.cap + ctx->d_rows.cap + ctx->d_rowcnt.cap;
+			size_t use_warps = nwarps;
+			if (per_warp*use_warps > have*8/10)
+				use_warps = std::max<size_t>(MB_WARPS_PER_BLOCK, (have*8/10/per_warp)/MB_WARPS_PER_BLOCK*MB_WARPS_PER_BLOCK);
+			nblocks = (uint32_t)(use_warps/MB_WARPS_PER_BLOCK);
+			ENSURE(ctx->d_fm, P.fm_stride*4*use_warps);
+			ENSURE(ctx->d_edge, P.edge_stride*16*use_warps);
+			ENSURE(ctx->d_rows, P.rows_stride*8*use_warps);
+			ENSURE(ctx->d_rowcnt, P.rowcnt_stride*use_warps);
+			P.h = ctx->hmm;
+			P.matchT = (const float *) ctx->d_matchT.p;
+			P.insT = (const float *) ctx->d_insT.p;
+			P.codes = (const uint8_t *) ctx->d_codes.p;
+			P.seqoff = (const uint64_t *) ctx->d_seqoff.p;
+			P.seqlen = (const uint32_t *) ctx->d_seqlen.p;
+			P.px = (const uint32_t *) ctx->d_px.p;
+			P.py = (const uint32_t *) ctx->d_py.p;
+			P.order = (const uint32_t *) ctx->d_order.p + bin_start[C];
+			P.nwork = (uint32_t) b.size();
+			P.counter = (uint32_t *) ctx->d_counters.p + C;
+			P.fm = (float *) ctx->d_fm.p;
+			P.edge = (float4 *) ctx->d_edge.p;
+			P.rows = (mb200_entry *) ctx->d_rows.p;
+			P.rowcnt = (uint8_t *) ctx->d_rowcnt.p;
+			P.rowoff = (uint32_t *) ctx->d_rowoff.p;
+			P.rowbase = (const uint64_t *) ctx->d_rowbase.p;
+			P.entries = (mb200_entry *) ctx->d_entries.p;
+			P.ent_cap = est_entries;
+			P.ent_cursor = (unsigned long long *) ctx->d_cursor.p;
+			P.entbase = (uint64_t *) ctx->d_entbase.p;
+			P.nnz = (uint32_t *) ctx->d_nnz.p;
+			P.ea = (float *) ctx->d_ea.p;
+			P.err = (int *) ctx->d_err.p;
+			if (dbg)
+				{
+				P.dbg_fwd = dbg->fwd; P.dbg_bwd = dbg->bwd; P.dbg_post = dbg->post; P.dbg_total = dbg->total;
+				}
+			if (!mb_post_dispatch(C, 0, dim3(nblocks), smem, st, &P, nullptr))
+				return mb_fail(ctx, MB200_EINVAL, "no kernel instance for C=%d", C);
+			CU(cudaGetLastError());
+			ctx->stats.kernel_launches++;
+			}
+		CU(cudaEventRecord(ctx->ev2, st));
+		int err = 0;
+		unsigned long long used = 0;
+		CU(cudaMemcpyAsync(&err, ctx->d_err.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+		CU(cudaMemcpyAsync(&used, ctx->d_cursor.p, sizeof(used), cudaMemcpyDeviceToHost, st));
+		CU(cudaStreamSynchronize(st));
+		ctx->stats.d2h_bytes += sizeof(int) + sizeof(used);
+		ctx->store_nnz = used;
+		if (err == MB200_ENOMEM && used > est_entries)
+			{
+			est_entries = used + used/16;     // the cursor counted everything: retry with the exact need
+			continue;
+			}
+		if (err == MB200_EOVERFLOW)
+			return mb_fail(ctx, MB200_EOVERFLOW, "a posterior row produced more than %d candidate entries", MB_CAP);
+		if (err != 0)
+			return mb_fail(ctx, err, "device error flag %d in k_posterior", err);
+		break;
+		}
+	if (ea_out)
+		{
+		CU(cudaMemcpyAsync(ea_out, ctx->d_ea.p, np*sizeof(float), cudaMemcpyDeviceToHost, st));
+		ctx->stats.d2h_bytes += np*sizeof(float);
+		}
+	CU(cudaEventRecord(ctx->ev3, st));
+	CU(cudaStreamSynchronize(st));
+	cudaEventElapsedTime(&ctx->stats.last_kernel_ms, ctx->ev1, ctx->ev2);
+	cudaEventElapsedTime(&ctx->stats.last_total_ms, ctx->ev0, ctx->ev3);
+	ctx->store_valid = true;
+	ctx->store_tr_valid = false;
+	ctx->store_packed = false;
+	return MB200_OK;
+	}
+
+int mb200_posteriors(mb200_ctx *ctx, uint32_t npairs, const uint32_t *pair_x, const uint32_t *pair_y,
+  uint32_t flags, float *ea_out)
+	{
+	if (!ctx || npairs == 0 || !pair_x || !pair_y)
+		return mb_fail(ctx, MB200_EINVAL, "mb200_posteriors: bad argument");
+	ctx->h_px.assign(pair_x, pair_x + npairs);
+	ctx->h_py.assign(pair_y, pair_y + npairs);
+	ctx->store_allpairs = false;
+	ctx->store_valid = false;
+	const int force_c = (int)((flags >> 8) & 0xff);
+	if (force_c > MB_MAX_C)
+		return mb_fail(ctx, MB200_EINVAL, "forced C %d > %d", force_c, MB_MAX_C);
+	return run_posteriors(ctx, ea_out, nullptr, force_c);
+	}
+
+} // extern "C"
+
+void mb_allpairs_list(uint32_t n, uint32_t p_lo, uint32_t p_hi, std::vector<uint32_t> &px, std::vector<uint32_t> &py)
+	{
+	px.clear();
+	py.clear();
+	uint32_t p = 0;
+	for (uint32_t i = 0; i < n; ++i)
+		{
+		const uint32_t rowlen = n - 1 - i;
+		if (p + rowlen <= p_lo)
+			{
+			p += rowlen;
+			continue;
+			}
+		for (uint32_t j = i + 1; j < n; ++j, ++p)
+			{
+			if (p >= p_hi)
+				return;
+			if (p >= p_lo)
+				{
+				px.push_back(i);
+				py.push_back(j);
+				}
+			}
+		}
+	}
+
+extern "C" {
+
+int mb200_posteriors_allpairs(mb200_ctx *ctx, uint32_t p_lo, uint32_t p_hi, float *ea_out)
+	{
+	if (!ctx || ctx->nseq < 2)
+		return mb_fail(ctx, MB200_EINVAL, "mb200_posteriors_allpairs: need >= 2 sequences");
+	const uint64_t npairs = (uint64_t) ctx->nseq*(ctx->nseq - 1)/2;
+	if (p_lo >= p_hi || p_hi > npairs)
+		return mb_fail(ctx, MB200_EINVAL, "pair range [%u,%u) invalid for %llu pairs", p_lo, p_hi,
+		  (unsigned long long) npairs);
+	mb_allpairs_list(ctx->nseq, p_lo, p_hi, ctx->h_px, ctx->h_py);
+	ctx->store_valid = false;
+	const int rc = run_posteriors(ctx, ea_out, nullptr, 0);
+	if (rc == MB200_OK)
+		{
+		ctx->store_allpairs = (p_lo == 0 && p_hi == npairs);
+		ctx->store_p_lo = p_lo;
+		ctx->store_p_hi = p_hi;
+		}
+	return rc;
+	}
+
+int mb200_calc_post_dense(mb200_ctx *ctx, uint32_t x, uint32_t y, float *post_out, float *fwd_m_out,
+  float *bwd_m_out, float *total_out)
+	{
+	if (!ctx || !post_out || x >= ctx->nseq || y >= ctx->nseq)
+		return mb_fail(ctx, MB200_EINVAL, "mb200_calc_post_dense: bad argument");
+	cudaSetDevice(ctx->device);
+	const size_t n = (size_t) ctx->h_len[x]*ctx->h_len[y];
+	ENSURE(ctx->d_dbg, (3*n + 4)*sizeof(float));
+	float *base = (float *) ctx->d_dbg.p;
+	PostDebug dbg = { base, base + n, base + 2*n, base + 3*n };
+	ctx->h_px.assign(1, x);
+	ctx->h_py.assign(1, y);
+	ctx->store_allpairs = false;
+	ctx->store_valid = false;
+	const int rc = run_posteriors(ctx, nullptr, &dbg, ctx->debug_force_c);
+	if (rc != MB200_OK)
+		return rc;
+	CU(cudaMemcpy(post_out, dbg.post, n*sizeof(float), cudaMemcpyDeviceToHost));
+	if (fwd_m_out)
+		CU(cudaMemcpy(fwd_m_out, dbg.fwd, n*sizeof(float), cudaMemcpyDeviceToHost));
+	if (bwd_m_out)
+		CU(cudaMemcpy(bwd_m_out, dbg.bwd, n*sizeof(float), cudaMemcpyDeviceToHost));
+	if (total_out)
+		CU(cudaMemcpy(total_out, dbg.total, sizeof(float), cudaMemcpyDeviceToHost));
+	return MB200_OK;
+	}
+
+// test hook: force the columns-per-lane of mb200_calc_post_dense (0 = automatic)
+int mb200_debug_force_c(mb200_ctx *ctx, int c)
+	{
+	if (!ctx || c < 0 || c > MB_MAX_C)
+		return MB200_EINVAL;
+	ctx->debug_force_c = c;
+	return MB200_OK;
+	}
+
+// test hook / tuning: expected sparse entries per posterior row used to size the entry pool
+int mb200_set_nnz_per_row_cap(mb200_ctx *ctx, uint32_t cap)
+	{
+	if (!ctx || cap == 0)
+		return MB200_EINVAL;
+	ctx->nnz_per_row_cap = cap;
+	return MB200_OK;
+	}
+
+// ------------------------------------------------------------------------------------------
+// store introspection
+int mb200_store_npairs(const mb200_ctx *ctx, uint32_t *npairs)
+	{
+	if (!ctx || !npairs)
+		return MB200_EINVAL;
+	*npairs = ctx->store_valid ? (uint32_t) ctx->h_px.size() : 0;
+	return MB200_OK;
+	}
+
+static int fetch_store_index(mb200_ctx *ctx)
+	{
+	if (!ctx->store_valid)
+		return mb_fail(ctx, MB200_EINVAL, "no posterior store (run mb200_posteriors first)");
+	const size_t np = ctx->h_px.size();
+	if (ctx->h_nnz.size() == np && ctx->h_index_valid)
+		return MB200_OK;
+	ctx->h_nnz.resize(np);
+	ctx->h_entbase.resize(np);
+	CU(cudaMemcpyAsync(ctx->h_nnz.data(), ctx->d_nnz.p, np*sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+	CU(cudaMemcpyAsync(ctx->h_entbase.data(), ctx->d_entbase.p, np*sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+	CU(cudaStreamSynchronize(ctx->stream));
+	ctx->h_index_valid = true;
+	return MB200_OK;
+	}
+
+int mb200_store_nnz(mb200_ctx *ctx, uint32_t *nnz_out, uint64_t *total_nnz)
+	{
+	if (!ctx)
+		return MB200_EINVAL;
+	cudaSetDevice(ctx->device);
+	ctx->h_index_valid = false;
+	const int rc = fetch_store_index(ctx);
+	if (rc != MB200_OK)
+		return rc;
+	uint64_t tot = 0;
+	for (size_t k = 0; k < ctx->h_nnz.size(); ++k)
+		{
+		if (nnz_out)
+			nnz_out[k] = ctx->h_nnz[k];
+		tot += ctx->h_nnz[k];
+		}
+	if (total_nnz)
+		*total_nnz = tot;
+	return MB200_OK;
+	}
+
+int mb200_export_pair(mb200_ctx *ctx, uint32_t pair, uint32_t *offsets, mb200_entry *entries)
+	{
+	if (!ctx || !offsets)
+		return mb_fail(ctx, MB200_EINVAL, "mb200_export_pair: bad argument");
+	cudaSetDevice(ctx->device);
+	ctx->h_index_valid = false;
+	int rc = fetch_store_index(ctx);
+	if (rc != MB200_OK)
+		return rc;
+	if (pair >= ctx->h_px.size())
+		return mb_fail(ctx, MB200_EINVAL, "pair %u out of range", pair);
+	const uint32_t LX = ctx->h_len[ctx->h_px[pair]];
+	CU(cudaMemcpy(offsets, (const uint32_t *) ctx->d_rowoff.p + ctx->h_rowbase[pair], (LX + 1)*sizeof(uint32_t),
+	  cudaMemcpyDeviceToHost));
+	if (entries && ctx->h_nnz[pair] > 0)
+		CU(cudaMemcpy(entries, (const mb200_entry *) ctx->d_entries.p + ctx->h_entbase[pair],
+		  (size_t) ctx->h_nnz[pair]*sizeof(mb200_entry), cudaMemcpyDeviceToHost));
+	return MB200_OK;
+	}
+
+} // extern "C"

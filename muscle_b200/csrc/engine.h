@@ -1,0 +1,66 @@
+// engine.h -- context layout shared by the host translation units of libmuscle_b200.so.
+#pragma once
+#include <vector>
+#include "launch.h"
+
+struct DevBuf
+	{
+	void  *p = nullptr;
+	size_t cap = 0;
+	int  ensure(size_t bytes);     // grow-only; 0 on success
+	void release();
+	};
+
+struct PostDebug { float *fwd, *bwd, *post, *total; };
+
+struct mb200_ctx
+	{
+	int device = 0;
+	cudaDeviceProp prop;
+	cudaStream_t stream = nullptr;
+	cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
+	char err[512];
+	mb200_stats stats = {};
+
+	// HMM
+	bool have_hmm = false;
+	MbHmm hmm = {};
+	uint8_t byte2class[256] = {};
+	DevBuf d_matchT, d_insT;
+
+	// sequences
+	uint32_t nseq = 0;
+	std::vector<uint8_t>  h_bytes;
+	std::vector<uint64_t> h_off;
+	std::vector<uint32_t> h_len;
+	DevBuf d_codes, d_seqoff, d_seqlen;
+
+	// the store: sparse posteriors of the listed pairs (replaces MPCFlat::m_SparsePosts1/2)
+	bool store_valid = false;
+	bool store_allpairs = false;      // holds all N(N-1)/2 pairs in reference order
+	uint32_t store_p_lo = 0, store_p_hi = 0;
+	bool store_packed = false;        // entries are packed in store order (entbase ascending, no holes)
+	bool store_tr_valid = false;      // transposed orientation + permutation built
+	uint64_t store_nnz = 0;
+	uint32_t nnz_per_row_cap = 12;    // entry pool sizing guess (retry with the exact count on overflow)
+	std::vector<uint32_t> h_px, h_py;
+	std::vector<uint64_t> h_rowbase;
+	std::vector<uint32_t> h_nnz;
+	std::vector<uint64_t> h_entbase;
+	bool h_index_valid = false;
+	DevBuf d_px, d_py, d_order, d_counters;
+	DevBuf d_rowoff, d_rowbase, d_entries, d_cursor, d_entbase, d_nnz, d_ea, d_err;
+	DevBuf d_entries2;                // second value buffer for the Jacobi update
+	DevBuf d_pack_off, d_pack_ent;    // packed image for exchange/export
+	// transposed orientation of every pair (rows = positions of Y) for the relax kernel
+	DevBuf d_tr_rowoff, d_tr_rowbase, d_tr_entries, d_tr_entbase, d_tr_perm;
+	DevBuf d_tmp, d_tmp2;
+
+	// per-warp scratch of the posterior kernel
+	DevBuf d_fm, d_edge, d_rows, d_rowcnt;
+	DevBuf d_dbg;
+	int debug_force_c = 0;
+	};
+
+int mb_fail(mb200_ctx *ctx, int code, const char *fmt, ...);
+void mb_allpairs_list(uint32_t n, uint32_t p_lo, uint32_t p_hi, std::vector<uint32_t> &px, std::vector<uint32_t> &py);

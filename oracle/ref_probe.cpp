@@ -219,14 +219,16 @@ double ref_mpc_posteriors_range(void *h, int lo, int hi, int threads)
 
 uint ref_mpc_pair_nnz(void *h, uint PairIndex)
 	{
-	return ((Handle *) h)->M.GetSparsePost(PairIndex).m_VecSize;
+	// m_Offsets[LX], not m_VecSize: UpdateFromPost (mysparsemx.cpp:87-113) never sets m_VecSize
+	MySparseMx &S = ((Handle *) h)->M.GetSparsePost(PairIndex);
+	return S.m_Offsets[S.m_LX];
 	}
 
 void ref_mpc_export(void *h, uint PairIndex, uint *Offsets, byte *Entries)
 	{
 	MySparseMx &S = ((Handle *) h)->M.GetSparsePost(PairIndex);
 	memcpy(Offsets, S.m_Offsets, (S.m_LX + 1)*sizeof(uint));
-	memcpy(Entries, S.m_ValueVec, size_t(S.m_VecSize)*8);
+	memcpy(Entries, S.m_ValueVec, size_t(S.m_Offsets[S.m_LX])*8);
 	}
 
 // inject a sparse posterior computed elsewhere (e.g. by the GPU engine) into the reference state

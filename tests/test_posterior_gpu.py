@@ -1,0 +1,126 @@
+"""GPU parity of the fused posterior kernel (through the C ABI) against the CPU oracle.
+
+Tolerances: Forward-M, Backward-M and the total log-probability are compared BIT-EXACT (every
+operation is an IEEE add/mul in the reference's order).  Posterior cells go through expf, where
+CUDA's expf and glibc's differ by <= 2 ulp, so dense posteriors are compared to 1e-6 absolute
+(north_star tolerance: 1e-4) and sparse membership is allowed to differ only for entries within
+1e-6 of the 0.01 cut.
+"""
+import os
+import numpy as np
+import pytest
+from conftest import GOLDEN
+from muscle_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+POST_TOL = 1e-6
+
+
+def _dense_check(engine, oracle, X, Y, force_c=0):
+	engine.set_seqs([X, Y])
+	post, fwd, bwd, tot = engine.calc_post_dense(0, 1, force_c=force_c)
+	f, b = oracle.fwd(X, Y), oracle.bwd(X, Y)
+	assert fwd.tobytes() == np.ascontiguousarray(f[1:, 1:, 0]).tobytes(), "Forward M not bit-exact"
+	assert bwd.tobytes() == np.ascontiguousarray(b[1:, 1:, 0]).tobytes(), "Backward M not bit-exact"
+	assert np.float32(tot) == np.float32(oracle.total(f, b)), "total not bit-exact"
+	p = oracle.post(X, Y)
+	assert np.abs(post - p).max() <= POST_TOL
+	assert ((post == 0) == (p == 0)).all(), "threshold at log(0.01) decided differently"
+	return post, p
+
+
+def _sparse_equal(off_g, ent_g, off_o, ent_o, tag=""):
+	"""identical pattern and values within POST_TOL; membership may differ only at the 0.01 cut"""
+	if (off_g == off_o).all() and (ent_g["col"] == ent_o["col"]).all():
+		assert np.abs(ent_g["p"] - ent_o["p"]).max(initial=0) <= POST_TOL, tag
+		return
+	LX = len(off_o) - 1
+	for i in range(LX):
+		g = {int(c): float(p) for p, c in ent_g[off_g[i]:off_g[i + 1]]}
+		o = {int(c): float(p) for p, c in ent_o[off_o[i]:off_o[i + 1]]}
+		for c in set(g) | set(o):
+			if c in g and c in o:
+				assert abs(g[c] - o[c]) <= POST_TOL, tag
+			else:
+				v = g.get(c, o.get(c))
+				assert abs(v - 0.01) <= POST_TOL, "%s row %d col %d only on one side with p=%g" % (tag, i, c, v)
+
+
+def test_kat_dense(engine, oracle):
+	z = np.load(os.path.join(GOLDEN, "kat_pairs.npz"))
+	for k in range(int(z["n"])):
+		X, Y = z["x%d" % k].tobytes(), z["y%d" % k].tobytes()
+		post, _ = _dense_check(engine, oracle, X, Y)
+		assert np.abs(post - z["post%d" % k]).max() <= POST_TOL     # golden from the compiled reference
+
+
+@pytest.mark.parametrize("force_c", [0, 1, 2, 3, 5, 8, 16])
+def test_family_dense_all_widths(engine, oracle, force_c):
+	seqs = synth.make_family(4, 140, 30, seed=31)
+	_dense_check(engine, oracle, seqs[0], seqs[1], force_c)
+	_dense_check(engine, oracle, seqs[2], seqs[3], force_c)
+
+
+def test_ragged_and_tiny(engine, oracle):
+	s = synth.make_family(3, 200, 10, seed=8)
+	for X, Y in [("A", "C"), ("A", s[0]), (s[0], "W"), (s[1][:33], s[2][:32]), (s[1][:32], s[2][:33]),
+	  (s[0][:64], s[1][:65]), ("ACDXBZ*", "acdefg")]:
+		_dense_check(engine, oracle, X, Y)
+
+
+def test_long_multistrip(engine, oracle):
+	# LY > 512 forces several 32*C column strips even at C=16
+	s = synth.make_family(2, 700, 40, seed=9)
+	_dense_check(engine, oracle, s[0], s[1])
+	_dense_check(engine, oracle, s[0][:100], s[1], force_c=4)
+
+
+def test_allpairs_c1_sparse_and_ea(engine, oracle):
+	seqs = synth.make_config("C1")
+	r = oracle.all_pairs(seqs, threads=0)
+	engine.set_seqs(seqs)
+	ea = engine.posteriors_allpairs()
+	n = len(seqs)
+	iu = np.triu_indices(n, 1)
+	assert np.abs(ea - r["ea"][iu]).max() <= 1e-6
+	nnz, tot = engine.store_nnz()
+	for k in range(len(nnz)):
+		off, ent = engine.export_pair(k, int(nnz[k]))
+		_sparse_equal(off, ent, r["row_off"][k], r["entries"][k], "pair %d" % k)
+	assert abs(int(tot) - int(r["nnz"].sum())) <= 4
+
+
+def test_family8_golden(engine):
+	z = np.load(os.path.join(GOLDEN, "family8.npz"))
+	seqs = [z["seq%d" % i].tobytes() for i in range(int(z["n"]))]
+	engine.set_seqs(seqs)
+	ea = engine.posteriors_allpairs()
+	n = len(seqs)
+	iu = np.triu_indices(n, 1)
+	assert np.abs(ea - z["ea"][iu]).max() <= 1e-6
+	nnz, _ = engine.store_nnz()
+	for k in range(len(nnz)):
+		off, ent = engine.export_pair(k, int(nnz[k]))
+		_sparse_equal(off, ent, z["off%d" % k], z["ent0_%d" % k], "pair %d" % k)
+
+
+def test_pair_list_api_and_order(engine, oracle):
+	seqs = synth.make_family(5, 80, 20, seed=77)
+	engine.set_seqs(seqs)
+	px, py = [3, 0, 2, 4], [1, 4, 3, 0]          # arbitrary orientation, X indexes rows
+	ea = engine.posteriors(px, py)
+	nnz, _ = engine.store_nnz()
+	for k, (x, y) in enumerate(zip(px, py)):
+		p = oracle.post(seqs[x], seqs[y])
+		off_o, ent_o = oracle.sparse(p)
+		off, ent = engine.export_pair(k, int(nnz[k]))
+		_sparse_equal(off, ent, off_o, ent_o)
+		assert abs(ea[k] - oracle.alnscore(p)/min(len(seqs[x]), len(seqs[y]))) <= 1e-6
+
+
+def test_errors(engine):
+	from muscle_b200.engine import MB200Error
+	engine.set_seqs(["ACD", "EFG"])
+	with pytest.raises(MB200Error):
+		engine.posteriors([0], [5])
