@@ -1,0 +1,307 @@
+#!/usr/bin/env python
+"""bench.py -- MPCFlat all-pairs posterior stage, DP cells/s (BASELINE.json metric).
+
+One "step" = one pass of the hot path (Forward + Backward + posterior + sparsify + EA for every
+sequence pair) over one synthetic protein family.  Default workload is BASELINE.json configs[2]
+(C3: 1000 proteins, mean length 350), the configuration the north_star's >=50x target is quoted
+on; it fits one B200.  With --gpus N the N(N-1)/2 pairs are sharded over the ranks in contiguous,
+cell-balanced ranges (strong scaling, no data-path collective in the timed region).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload C3]
+
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for the definition of every field.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np  # noqa: E402
+
+METRIC = "pair-HMM DP cells/sec (all-pairs Fwd+Bwd+posterior)"
+UNIT = "cells/s"
+ALGO_BYTES_PER_CELL = 12.0      # 4 B write + 4 B read of Forward-M, 4 B posterior
+ISSUE_FLOP_PER_CELL = 243.0
+
+
+def load_peaks():
+	p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+	if os.path.exists(p):
+		with open(p) as f:
+			d = json.load(f)
+		return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+	return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler(threading.Thread):
+	"""nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+	Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+	  "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+	  "clocks_event_reasons.sw_power_cap")
+
+	def __init__(self, index):
+		super().__init__(daemon=True)
+		self.index = index
+		self.rows = []
+		self.stop_flag = False
+		self.proc = None
+
+	def run(self):
+		try:
+			self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+			  "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+			for line in self.proc.stdout:
+				self.rows.append(line.strip())
+				if self.stop_flag:
+					break
+		except Exception:
+			pass
+
+	def finish(self):
+		self.stop_flag = True
+		if self.proc is not None:
+			try:
+				self.proc.terminate()
+			except Exception:
+				pass
+		sm, mx, reasons = [], [], set()
+		names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+		for r in self.rows:
+			f = [x.strip() for x in r.split(",")]
+			if len(f) < 7:
+				continue
+			try:
+				sm.append(float(f[0]))
+				mx.append(float(f[1]))
+			except ValueError:
+				continue
+			for k, nm in enumerate(names):
+				if f[3 + k].lower().startswith("active"):
+					reasons.add(nm)
+		if not sm:
+			return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+		# median over the samples taken under load (upper half of the observed clocks)
+		return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+		  "samples": len(sm)}
+
+
+def shard_ranges(seqs, world):
+	"""contiguous ranges of the row-major pair list with ~equal DP cells per rank"""
+	L = np.array([len(s) for s in seqs], np.float64)
+	n = len(seqs)
+	iu, ju = np.triu_indices(n, 1)
+	cost = np.cumsum(L[iu]*L[ju])
+	total = cost[-1]
+	cuts = [0]
+	for r in range(1, world):
+		cuts.append(int(np.searchsorted(cost, total*r/world)))
+	cuts.append(len(iu))
+	cells = [float((cost[cuts[r + 1] - 1] - (cost[cuts[r] - 1] if cuts[r] > 0 else 0.0))) for r in range(world)]
+	return [(cuts[r], cuts[r + 1]) for r in range(world)], cells, float(total)
+
+
+def cpu_reference_run(seqs, target_cells, threads=0, seconds=None):
+	"""Time the compiled reference (oracle/_ref) -- or the C port when it is absent -- on a bounded
+	sample (a prefix of the row-major pair list holding ~target_cells DP cells).  With `seconds`
+	the sample is sized from a short calibration run so that it takes about that long."""
+	if seconds is not None:
+		probe = cpu_reference_run(seqs, 2.0e8, threads)
+		target_cells = max(2.0e8, probe["value"]*seconds)
+	from conftest import load_tables
+	from oracle import pyoracle
+	L = np.array([len(s) for s in seqs], np.float64)
+	n = len(seqs)
+	iu, ju = np.triu_indices(n, 1)
+	cost = np.cumsum(L[iu]*L[ju])
+	hi = int(min(len(iu), max(1, np.searchsorted(cost, target_cells) + 1)))
+	cells = float(cost[hi - 1])
+	if os.path.exists(pyoracle.REF_SO):
+		R = pyoracle.Ref()
+		M = R.mpc(seqs)
+		secs = M.posteriors_range(0, hi, threads)
+		M.close()
+		kind, cores = "reference", R.threads if threads <= 0 else threads
+	else:
+		O = pyoracle.Oracle(load_tables())
+		t0 = time.time()
+		O.all_pairs(seqs, 0, hi, threads=threads, want_sparse=False)
+		secs = time.time() - t0
+		kind, cores = "port", (os.cpu_count() if threads <= 0 else threads)
+	return {"value": cells/secs, "unit": UNIT, "cores": int(cores), "kind": kind, "seconds": secs,
+	  "sample": "first %d of %d pairs (row-major), %.3g cells, OpenMP dynamic schedule, all host threads" %
+	  (hi, len(iu), cells)}
+
+
+def main():
+	ap = argparse.ArgumentParser()
+	ap.add_argument("--gpus", type=int, default=1)
+	ap.add_argument("--steps", type=int, default=3)
+	ap.add_argument("--warmup", type=int, default=3)
+	ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+	ap.add_argument("--workload", default="C3")
+	ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of the baseline sample")
+	ap.add_argument("--no-cpu-baseline", action="store_true")
+	args = ap.parse_args()
+
+	rank = int(os.environ.get("RANK", "0"))
+	world = int(os.environ.get("WORLD_SIZE", "1"))
+	local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+	from muscle_b200 import synth
+	seqs = synth.make_config(args.workload)
+	n = len(seqs)
+	lens = [len(s) for s in seqs]
+	config = {"workload": "%s: %d synthetic proteins, mean length %.0f (muscle_b200.synth seed %d), all %d pairs" %
+	  (args.workload, n, float(np.mean(lens)), synth.CONFIGS[args.workload][3], n*(n - 1)//2),
+	  "stage": "MPCFlat::CalcPosteriors (Fwd+Bwd+posterior+sparsify+EA)",
+	  "sharding": "contiguous cell-balanced pair ranges, %d rank(s)" % world,
+	  "l2": "per-step working set (Forward-M spill + sparse output, >10 GB) exceeds the 126 MB L2"}
+
+	# ------------------------------------------------------------------ reference arm
+	if args.impl == "reference":
+		if rank != 0:
+			return
+		probe = cpu_reference_run(seqs, 2.0e8)
+		target = max(2.0e8, probe["value"]*args.cpu_seconds)     # each step ~cpu_seconds of host time
+		vals = []
+		last = None
+		for _ in range(args.warmup):
+			cpu_reference_run(seqs, target/8)
+		t0 = time.time()
+		for _ in range(args.steps):
+			last = cpu_reference_run(seqs, target)
+			vals.append(last["value"])
+		wall = time.time() - t0
+		v = float(np.mean(vals))
+		out = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
+		  "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3*wall/max(1, args.steps),
+		  "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+		  "config": config,
+		  "cpu_baseline": {"value": v, "unit": UNIT, "cores": last["cores"], "kind": last["kind"], "sample": last["sample"]},
+		  "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+		print(json.dumps(out))
+		return
+
+	# ------------------------------------------------------------------ our arm
+	import torch
+	import torch.distributed as dist
+	if not torch.cuda.is_available():
+		raise SystemExit("bench.py: no CUDA device; libmuscle_b200 has no CPU path")
+	torch.cuda.set_device(local_rank)
+	if world > 1:
+		dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+	from conftest import load_tables
+	from muscle_b200.engine import Engine
+	eng = Engine(local_rank)
+	eng.set_hmm(load_tables())
+	eng.set_seqs(seqs)
+	ranges, cells_per_rank, total_cells = shard_ranges(seqs, world)
+	p_lo, p_hi = ranges[rank]
+	my_cells = cells_per_rank[rank]
+
+	def barrier():
+		if world > 1:
+			dist.barrier()
+		torch.cuda.synchronize()
+
+	def step_resident():
+		# inputs (sequences, tables, pair list) already in HBM; EA stays on the device
+		eng.posteriors_allpairs(p_lo, p_hi, want_ea=False)
+		s = eng.stats()
+		return s["last_total_ms"], s["last_kernel_ms"]
+
+	def step_e2e():
+		# public API with host buffers: sequences up, EA matrix slice down, every step
+		eng.set_seqs(seqs)
+		ea = eng.posteriors_allpairs(p_lo, p_hi, want_ea=True)
+		s = eng.stats()
+		return float(ea[0]), s["h2d_bytes"], s["d2h_bytes"]
+
+	for _ in range(max(3, args.warmup)):
+		step_resident()
+	launches0 = eng.stats()["kernel_launches"]
+	sampler = ClockSampler(local_rank)
+	if rank == 0:
+		sampler.start()
+	barrier()
+	t0 = time.time()
+	dev_ms = 0.0
+	kern_ms = 0.0
+	for _ in range(args.steps):
+		tot, k = step_resident()
+		dev_ms += tot
+		kern_ms += k
+	barrier()
+	wall = time.time() - t0
+	clocks = sampler.finish() if rank == 0 else None
+	launches = eng.stats()["kernel_launches"] - launches0
+
+	# end to end through the host-facing call
+	step_e2e()
+	barrier()
+	t1 = time.time()
+	h2d = d2h = 0
+	for _ in range(args.steps):
+		_, h2d, d2h = step_e2e()
+	barrier()
+	wall_e2e = time.time() - t1
+
+	# max over ranks (device time of the timed region, wall of both loops)
+	tv = torch.tensor([dev_ms, kern_ms, wall, wall_e2e], dtype=torch.float64, device="cuda")
+	if world > 1:
+		dist.all_reduce(tv, op=dist.ReduceOp.MAX)
+	dev_ms_max, kern_ms_max, wall_max, wall_e2e_max = [float(x) for x in tv.tolist()]
+
+	if rank == 0:
+		steps = args.steps
+		# value: whole-job cells over the max-over-ranks time of the timed region (barrier to barrier)
+		value = total_cells*steps/wall_max
+		e2e_value = total_cells*steps/wall_e2e_max
+		peak, peak_src = load_peaks()
+		# dominant kernel k_posterior<C> (one launch per column-width bin): live CUDA-event time of the
+		# launches of this rank, algorithmic bytes = 12 B/cell x cells of this rank
+		achieved = ALGO_BYTES_PER_CELL*my_cells*steps/(kern_ms*1e-3)/1e9
+		traffic = None
+		tp = os.path.join(ROOT, "profiles", "traffic_bytes_per_cell.json")
+		if os.path.exists(tp):
+			try:
+				with open(tp) as f:
+					traffic = json.load(f).get("dram_bytes_per_cell", None)
+				if traffic is not None:
+					traffic = traffic*my_cells
+			except Exception:
+				traffic = None
+		out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": max(3, args.warmup),
+		  "ms_per_step": 1e3*wall_max/steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+		  "dtype": "f32", "data": "synthetic", "config": config,
+		  "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+		    "what": "mb200_set_seqs(host bytes) + mb200_posteriors_allpairs -> EA on host; sparse store stays in HBM for the next stage"},
+		  "gpu_launches": int(launches),
+		  "clocks": clocks,
+		  "roofline": {"bound": "hbm", "kernel": "k_posterior<C>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+		    "frac": achieved/peak, "traffic": traffic, "peak_source": peak_src,
+		    "algorithmic_bytes_per_cell": ALGO_BYTES_PER_CELL,
+		    "kernel_ms_per_step": kern_ms/steps,
+		    "note": "kernel is fp32-issue bound, not HBM bound (SURVEY.md 8d): see issue_gflops",
+		    "issue_gflops": ISSUE_FLOP_PER_CELL*my_cells*steps/(kern_ms*1e-3)/1e9},
+		  "device_ms_per_step": dev_ms_max/steps}
+		if not args.no_cpu_baseline and world == 1:
+			out["cpu_baseline"] = cpu_reference_run(seqs, 0, seconds=args.cpu_seconds)
+		print(json.dumps(out))
+	if world > 1:
+		dist.barrier()
+		dist.destroy_process_group()
+	eng.close()
+
+
+if __name__ == "__main__":
+	main()

@@ -50,8 +50,13 @@ struct LogAdd
 		const float d = fabsf(__fsub_rn(x, y));
 		const float lo = fminf(x, y);
 		const float hi = fmaxf(x, y);
-		const int idx = (d > 1.0f) + (d > 2.5f) + (d > 4.5f);
-		const float4 c = coef[idx];
+		// piece index by a 2-step binary search (FSETP, FSEL, FSETP, SEL, predicated add)
+		const bool p2 = d > 2.5f;
+		const float thr = p2 ? 4.5f : 1.0f;
+		const float4 *a = p2 ? coef + 2 : coef;
+		if (d > thr)
+			a += 1;
+		const float4 c = *a;
 		float p = ADD(MUL(c.x, d), c.y);
 		p = ADD(MUL(p, d), c.z);
 		p = ADD(MUL(p, d), c.w);

@@ -96,6 +96,11 @@ int mb200_create(int device, mb200_ctx **out)
 	cudaEventCreate(&ctx->ev1);
 	cudaEventCreate(&ctx->ev2);
 	cudaEventCreate(&ctx->ev3);
+	for (int k = 0; k < mb200_ctx::kStreams; ++k)
+		{
+		cudaStreamCreateWithFlags(&ctx->aux[k], cudaStreamNonBlocking);
+		cudaEventCreateWithFlags(&ctx->aux_done[k], cudaEventDisableTiming);
+		}
 	*out = ctx;
 	return MB200_OK;
 	}
@@ -107,13 +112,23 @@ void mb200_destroy(mb200_ctx *ctx)
 	cudaSetDevice(ctx->device);
 	cudaStreamSynchronize(ctx->stream);
 	DevBuf *bufs[] = { &ctx->d_matchT, &ctx->d_insT, &ctx->d_codes, &ctx->d_seqoff, &ctx->d_seqlen, &ctx->d_px,
-	  &ctx->d_py, &ctx->d_order, &ctx->d_counters, &ctx->d_fm, &ctx->d_edge, &ctx->d_rows, &ctx->d_rowcnt,
+	  &ctx->d_py, &ctx->d_order, &ctx->d_counters,
 	  &ctx->d_rowoff, &ctx->d_rowbase, &ctx->d_entries, &ctx->d_cursor, &ctx->d_entbase, &ctx->d_nnz,
 	  &ctx->d_ea, &ctx->d_err, &ctx->d_dbg, &ctx->d_pack_off, &ctx->d_pack_ent, &ctx->d_entries2,
 	  &ctx->d_tr_rowoff, &ctx->d_tr_rowbase, &ctx->d_tr_entries, &ctx->d_tr_entbase, &ctx->d_tr_perm,
 	  &ctx->d_tmp, &ctx->d_tmp2 };
 	for (DevBuf *b : bufs)
 		b->release();
+	for (int c = 0; c <= MB_MAX_C; ++c)
+		{
+		ctx->d_fm[c].release(); ctx->d_edge[c].release(); ctx->d_rows[c].release(); ctx->d_rowcnt[c].release();
+		}
+	for (int k = 0; k < mb200_ctx::kStreams; ++k)
+		{
+		cudaStreamSynchronize(ctx->aux[k]);
+		cudaStreamDestroy(ctx->aux[k]);
+		cudaEventDestroy(ctx->aux_done[k]);
+		}
 	cudaEventDestroy(ctx->ev0);
 	cudaEventDestroy(ctx->ev1);
 	cudaEventDestroy(ctx->ev2);
@@ -239,9 +254,12 @@ int mb200_set_seqs(mb200_ctx *ctx, uint32_t nseq, const uint8_t *bytes, const ui
 	ENSURE(ctx->d_seqlen, nseq*sizeof(uint32_t));
 	CU(cudaMemcpyAsync(ctx->d_seqoff.p, ctx->h_off.data(), (nseq + 1)*sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
 	CU(cudaMemcpyAsync(ctx->d_seqlen.p, ctx->h_len.data(), nseq*sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
-	ctx->stats.h2d_bytes = (nseq + 1)*sizeof(uint64_t) + nseq*sizeof(uint32_t);
+	ctx->stats.h2d_bytes = (nseq + 1)*sizeof(uint64_t) + nseq*sizeof(uint32_t);   // counters restart at set_seqs
+	ctx->stats.d2h_bytes = 0;
 	ctx->store_valid = false;
 	ctx->store_allpairs = false;
+	ctx->plan_valid = false;
+	ctx->last_used_entries = 0;
 	if (ctx->have_hmm)
 		return recode_seqs(ctx);
 	CU(cudaStreamSynchronize(ctx->stream));
@@ -250,20 +268,16 @@ int mb200_set_seqs(mb200_ctx *ctx, uint32_t nseq, const uint8_t *bytes, const ui
 
 // ------------------------------------------------------------------------------------------
 // posterior stage
-static int run_posteriors(mb200_ctx *ctx, float *ea_out, const PostDebug *dbg, int force_c)
+// Plan = everything that depends only on the pair list: per-pair row bases, the column-width
+// bins and the longest-first work order.  Cached across calls with the same pair list so that a
+// repeated mb200_posteriors_allpairs() moves no host data.
+static int prepare_plan(mb200_ctx *ctx, int force_c)
 	{
 	const uint32_t np = (uint32_t) ctx->h_px.size();
-	if (!ctx->have_hmm || ctx->nseq == 0)
-		return mb_fail(ctx, MB200_EINVAL, "mb200_posteriors: call mb200_set_hmm and mb200_set_seqs first");
-	cudaSetDevice(ctx->device);
 	cudaStream_t st = ctx->stream;
-	ctx->stats.h2d_bytes = 0;
-	ctx->stats.d2h_bytes = 0;
-	CU(cudaEventRecord(ctx->ev0, st));
-
-	// per-pair geometry, reference overflow guard (fwdflat3.cpp:17-18)
 	std::vector<uint64_t> rowbase(np + 1);
 	uint64_t cells = 0, rows_total = 0, est_entries = 0;
+	// per-pair geometry, reference overflow guard (fwdflat3.cpp:17-18)
 	for (uint32_t k = 0; k < np; ++k)
 		{
 		const uint32_t x = ctx->h_px[k], y = ctx->h_py[k];
@@ -280,7 +294,8 @@ static int run_posteriors(mb200_ctx *ctx, float *ea_out, const PostDebug *dbg, i
 		}
 	rowbase[np] = rows_total;
 	ctx->h_rowbase = rowbase;
-	ctx->stats.cells = cells;
+	ctx->plan_cells = cells;
+	ctx->plan_est_entries = est_entries;
 
 	ENSURE(ctx->d_px, np*sizeof(uint32_t));
 	ENSURE(ctx->d_py, np*sizeof(uint32_t));
@@ -298,34 +313,61 @@ static int run_posteriors(mb200_ctx *ctx, float *ea_out, const PostDebug *dbg, i
 	CU(cudaMemcpyAsync(ctx->d_rowbase.p, rowbase.data(), (np + 1)*sizeof(uint64_t), cudaMemcpyHostToDevice, st));
 	ctx->stats.h2d_bytes += 2ull*np*sizeof(uint32_t) + (np + 1)*sizeof(uint64_t);
 
-	// bin pairs by C = columns per lane; inside a bin longest X first
-	std::vector<std::vector<uint32_t>> bins(MB_MAX_C + 1);
+	// bin pairs by C = columns per lane; inside a bin most cells first
+	auto &bins = ctx->plan_bins;
+	bins.assign(MB_MAX_C + 1, std::vector<uint32_t>());
+	std::vector<uint64_t> cost(np);
 	for (uint32_t k = 0; k < np; ++k)
 		{
 		const uint32_t LY = ctx->h_len[ctx->h_py[k]];
-		int C = force_c > 0 ? force_c : (int) std::min<uint32_t>(MB_MAX_C, (LY + 31)/32);
+		const int C = force_c > 0 ? force_c : (int) std::min<uint32_t>(MB_MAX_C, (LY + 31)/32);
 		bins[C].push_back(k);
+		cost[k] = (uint64_t) ctx->h_len[ctx->h_px[k]]*LY;
 		}
 	std::vector<uint32_t> order;
 	order.reserve(np);
-	std::vector<uint32_t> bin_start(MB_MAX_C + 2, 0);
+	ctx->plan_bin_start.assign(MB_MAX_C + 2, 0);
+	ctx->plan_lxmax.assign(MB_MAX_C + 1, 0);
+	ctx->plan_lymax.assign(MB_MAX_C + 1, 0);
 	for (int C = 1; C <= MB_MAX_C; ++C)
 		{
 		auto &b = bins[C];
-		std::stable_sort(b.begin(), b.end(), [&](uint32_t a, uint32_t c2)
-			{
-			const uint64_t ca = (uint64_t) ctx->h_len[ctx->h_px[a]]*ctx->h_len[ctx->h_py[a]];
-			const uint64_t cb = (uint64_t) ctx->h_len[ctx->h_px[c2]]*ctx->h_len[ctx->h_py[c2]];
-			return ca > cb;
-			});
-		bin_start[C] = (uint32_t) order.size();
+		std::stable_sort(b.begin(), b.end(), [&](uint32_t a, uint32_t c2) { return cost[a] > cost[c2]; });
+		ctx->plan_bin_start[C] = (uint32_t) order.size();
 		order.insert(order.end(), b.begin(), b.end());
+		for (uint32_t k : b)
+			{
+			ctx->plan_lxmax[C] = std::max(ctx->plan_lxmax[C], ctx->h_len[ctx->h_px[k]]);
+			ctx->plan_lymax[C] = std::max(ctx->plan_lymax[C], ctx->h_len[ctx->h_py[k]]);
+			}
 		}
-	bin_start[MB_MAX_C + 1] = (uint32_t) order.size();
+	ctx->plan_bin_start[MB_MAX_C + 1] = (uint32_t) order.size();
 	CU(cudaMemcpyAsync(ctx->d_order.p, order.data(), np*sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+	CU(cudaStreamSynchronize(st));     // host vectors above go out of scope
 	ctx->stats.h2d_bytes += np*sizeof(uint32_t);
-	CU(cudaMemsetAsync(ctx->d_counters.p, 0, (MB_MAX_C + 1)*sizeof(uint32_t), st));
-	CU(cudaMemsetAsync(ctx->d_err.p, 0, sizeof(int), st));
+	ctx->plan_valid = true;
+	ctx->plan_force_c = force_c;
+	return MB200_OK;
+	}
+
+static int run_posteriors(mb200_ctx *ctx, float *ea_out, const PostDebug *dbg, int force_c)
+	{
+	const uint32_t np = (uint32_t) ctx->h_px.size();
+	if (!ctx->have_hmm || ctx->nseq == 0)
+		return mb_fail(ctx, MB200_EINVAL, "mb200_posteriors: call mb200_set_hmm and mb200_set_seqs first");
+	cudaSetDevice(ctx->device);
+	cudaStream_t st = ctx->stream;
+	CU(cudaEventRecord(ctx->ev0, st));
+	if (!ctx->plan_valid || ctx->plan_force_c != force_c)
+		{
+		const int rc = prepare_plan(ctx, force_c);
+		if (rc != MB200_OK)
+			return rc;
+		}
+	ctx->stats.cells = ctx->plan_cells;
+	uint64_t est_entries = std::max(ctx->plan_est_entries, ctx->last_used_entries);
+	const auto &bins = ctx->plan_bins;
+	const auto &bin_start = ctx->plan_bin_start;
 
 	for (int attempt = 0; attempt < 3; ++attempt)
 		{
@@ -334,23 +376,24 @@ static int run_posteriors(mb200_ctx *ctx, float *ea_out, const PostDebug *dbg, i
 		CU(cudaMemsetAsync(ctx->d_counters.p, 0, (MB_MAX_C + 1)*sizeof(uint32_t), st));
 		CU(cudaMemsetAsync(ctx->d_err.p, 0, sizeof(int), st));
 		CU(cudaEventRecord(ctx->ev1, st));
-		for (int C = 1; C <= MB_MAX_C; ++C)
+		for (int k = 0; k < mb200_ctx::kStreams; ++k)
+			CU(cudaStreamWaitEvent(ctx->aux[k], ctx->ev1, 0));
+		// widest bins first: they hold most of the work, the narrow ones fill the tails
+		int nlaunched = 0;
+		for (int C = MB_MAX_C; C >= 1; --C)
 			{
 			const auto &b = bins[C];
 			if (b.empty())
 				continue;
-			uint32_t lxmax = 0, lymax = 0;
-			for (uint32_t k : b)
-				{
-				lxmax = std::max(lxmax, ctx->h_len[ctx->h_px[k]]);
-				lymax = std::max(lymax, ctx->h_len[ctx->h_py[k]]);
-				}
+			cudaStream_t ks = ctx->aux[nlaunched % mb200_ctx::kStreams];
+			++nlaunched;
+			const uint32_t lxmax = ctx->plan_lxmax[C], lymax = ctx->plan_lymax[C];
 			const uint32_t W = 32u*C;
 			const uint32_t nstrips = (lymax + W - 1)/W;
 			int smem_static = 0, occ = 0;
-			mb_post_dispatch(C, 2, dim3(), 0, st, nullptr, &smem_static);
+			mb_post_dispatch(C, 2, dim3(), 0, ks, nullptr, &smem_static);
 			const size_t smem = (size_t) smem_static + (size_t) ctx->hmm.K*ctx->hmm.KS*sizeof(float);
-			mb_post_dispatch(C, 1, dim3(), smem, st, nullptr, &occ);
+			mb_post_dispatch(C, 1, dim3(), smem, ks, nullptr, &occ);
 			if (occ <= 0)
 				return mb_fail(ctx, MB200_ECUDA, "k_posterior<%d> cannot be resident (smem %zu)", C, smem);
 			uint32_t nblocks = (uint32_t) occ*ctx->prop.multiProcessorCount;
@@ -369,15 +412,15 @@ static int run_posteriors(mb200_ctx *ctx, float *ea_out, const PostDebug *dbg, i
 			size_t per_warp = P.fm_stride*4 + P.edge_stride*16 + P.rows_stride*8 + P.rowcnt_stride;
 			size_t free_b = 0, total_b = 0;
 			cudaMemGetInfo(&free_b, &total_b);
-			const size_t have = free_b + ctx->d_fm.cap + ctx->d_edge.cap + ctx->d_rows.cap + ctx->d_rowcnt.cap;
+			const size_t have = free_b + ctx->d_fm[C].cap + ctx->d_edge[C].cap + ctx->d_rows[C].cap + ctx->d_rowcnt[C].cap;
 			size_t use_warps = nwarps;
 			if (per_warp*use_warps > have*8/10)
 				use_warps = std::max<size_t>(MB_WARPS_PER_BLOCK, (have*8/10/per_warp)/MB_WARPS_PER_BLOCK*MB_WARPS_PER_BLOCK);
 			nblocks = (uint32_t)(use_warps/MB_WARPS_PER_BLOCK);
-			ENSURE(ctx->d_fm, P.fm_stride*4*use_warps);
-			ENSURE(ctx->d_edge, P.edge_stride*16*use_warps);
-			ENSURE(ctx->d_rows, P.rows_stride*8*use_warps);
-			ENSURE(ctx->d_rowcnt, P.rowcnt_stride*use_warps);
+			ENSURE(ctx->d_fm[C], P.fm_stride*4*use_warps);
+			ENSURE(ctx->d_edge[C], P.edge_stride*16*use_warps);
+			ENSURE(ctx->d_rows[C], P.rows_stride*8*use_warps);
+			ENSURE(ctx->d_rowcnt[C], P.rowcnt_stride*use_warps);
 			P.h = ctx->hmm;
 			P.matchT = (const float *) ctx->d_matchT.p;
 			P.insT = (const float *) ctx->d_insT.p;
@@ -389,10 +432,10 @@ static int run_posteriors(mb200_ctx *ctx, float *ea_out, const PostDebug *dbg, i
 			P.order = (const uint32_t *) ctx->d_order.p + bin_start[C];
 			P.nwork = (uint32_t) b.size();
 			P.counter = (uint32_t *) ctx->d_counters.p + C;
-			P.fm = (float *) ctx->d_fm.p;
-			P.edge = (float4 *) ctx->d_edge.p;
-			P.rows = (mb200_entry *) ctx->d_rows.p;
-			P.rowcnt = (uint8_t *) ctx->d_rowcnt.p;
+			P.fm = (float *) ctx->d_fm[C].p;
+			P.edge = (float4 *) ctx->d_edge[C].p;
+			P.rows = (mb200_entry *) ctx->d_rows[C].p;
+			P.rowcnt = (uint8_t *) ctx->d_rowcnt[C].p;
 			P.rowoff = (uint32_t *) ctx->d_rowoff.p;
 			P.rowbase = (const uint64_t *) ctx->d_rowbase.p;
 			P.entries = (mb200_entry *) ctx->d_entries.p;
@@ -406,10 +449,15 @@ static int run_posteriors(mb200_ctx *ctx, float *ea_out, const PostDebug *dbg, i
 				{
 				P.dbg_fwd = dbg->fwd; P.dbg_bwd = dbg->bwd; P.dbg_post = dbg->post; P.dbg_total = dbg->total;
 				}
-			if (!mb_post_dispatch(C, 0, dim3(nblocks), smem, st, &P, nullptr))
+			if (!mb_post_dispatch(C, 0, dim3(nblocks), smem, ks, &P, nullptr))
 				return mb_fail(ctx, MB200_EINVAL, "no kernel instance for C=%d", C);
 			CU(cudaGetLastError());
 			ctx->stats.kernel_launches++;
+			}
+		for (int k = 0; k < mb200_ctx::kStreams; ++k)
+			{
+			CU(cudaEventRecord(ctx->aux_done[k], ctx->aux[k]));
+			CU(cudaStreamWaitEvent(st, ctx->aux_done[k], 0));
 			}
 		CU(cudaEventRecord(ctx->ev2, st));
 		int err = 0;
@@ -422,6 +470,7 @@ static int run_posteriors(mb200_ctx *ctx, float *ea_out, const PostDebug *dbg, i
 		if (err == MB200_ENOMEM && used > est_entries)
 			{
 			est_entries = used + used/16;     // the cursor counted everything: retry with the exact need
+			ctx->last_used_entries = est_entries;
 			continue;
 			}
 		if (err == MB200_EOVERFLOW)
@@ -454,6 +503,8 @@ int mb200_posteriors(mb200_ctx *ctx, uint32_t npairs, const uint32_t *pair_x, co
 	ctx->h_py.assign(pair_y, pair_y + npairs);
 	ctx->store_allpairs = false;
 	ctx->store_valid = false;
+	ctx->plan_valid = false;
+	ctx->plan_is_allpairs = false;
 	const int force_c = (int)((flags >> 8) & 0xff);
 	if (force_c > MB_MAX_C)
 		return mb_fail(ctx, MB200_EINVAL, "forced C %d > %d", force_c, MB_MAX_C);
@@ -498,8 +549,15 @@ int mb200_posteriors_allpairs(mb200_ctx *ctx, uint32_t p_lo, uint32_t p_hi, floa
 	if (p_lo >= p_hi || p_hi > npairs)
 		return mb_fail(ctx, MB200_EINVAL, "pair range [%u,%u) invalid for %llu pairs", p_lo, p_hi,
 		  (unsigned long long) npairs);
-	mb_allpairs_list(ctx->nseq, p_lo, p_hi, ctx->h_px, ctx->h_py);
+	if (!(ctx->plan_valid && ctx->plan_is_allpairs && ctx->store_p_lo == p_lo && ctx->store_p_hi == p_hi))
+		{
+		mb_allpairs_list(ctx->nseq, p_lo, p_hi, ctx->h_px, ctx->h_py);
+		ctx->plan_valid = false;
+		}
 	ctx->store_valid = false;
+	ctx->plan_is_allpairs = true;
+	ctx->store_p_lo = p_lo;
+	ctx->store_p_hi = p_hi;
 	const int rc = run_posteriors(ctx, ea_out, nullptr, 0);
 	if (rc == MB200_OK)
 		{
@@ -524,6 +582,8 @@ int mb200_calc_post_dense(mb200_ctx *ctx, uint32_t x, uint32_t y, float *post_ou
 	ctx->h_py.assign(1, y);
 	ctx->store_allpairs = false;
 	ctx->store_valid = false;
+	ctx->plan_valid = false;
+	ctx->plan_is_allpairs = false;
 	const int rc = run_posteriors(ctx, nullptr, &dbg, ctx->debug_force_c);
 	if (rc != MB200_OK)
 		return rc;

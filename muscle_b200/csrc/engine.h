@@ -56,8 +56,18 @@ struct mb200_ctx
 	DevBuf d_tr_rowoff, d_tr_rowbase, d_tr_entries, d_tr_entbase, d_tr_perm;
 	DevBuf d_tmp, d_tmp2;
 
+	// cached launch plan of the posterior stage (depends only on the pair list)
+	bool plan_valid = false, plan_is_allpairs = false;
+	int plan_force_c = 0;
+	uint64_t plan_cells = 0, plan_est_entries = 0, last_used_entries = 0;
+	std::vector<std::vector<uint32_t>> plan_bins;
+	std::vector<uint32_t> plan_bin_start, plan_lxmax, plan_lymax;
+
 	// per-warp scratch of the posterior kernel
-	DevBuf d_fm, d_edge, d_rows, d_rowcnt;
+	DevBuf d_fm[MB_MAX_C + 1], d_edge[MB_MAX_C + 1], d_rows[MB_MAX_C + 1], d_rowcnt[MB_MAX_C + 1];   // per bin
+	static constexpr int kStreams = 4;          // column-width bins run concurrently to overlap their tails
+	cudaStream_t aux[kStreams] = {};
+	cudaEvent_t aux_done[kStreams] = {};
 	DevBuf d_dbg;
 	int debug_force_c = 0;
 	};

@@ -102,8 +102,11 @@ __device__ __forceinline__ void bwd_cells(const MbHmm &h, const LogAdd &la, cons
 		}
 	}
 
+// resident CTAs per SM the register budget is tuned for (4 warps each)
+template <int C> struct PostOcc { static constexpr int kBlocks = C <= 5 ? 5 : (C <= 8 ? 4 : 3); };
+
 template <int C>
-__global__ void __launch_bounds__(32*MB_WARPS_PER_BLOCK)
+__global__ void __launch_bounds__(32*MB_WARPS_PER_BLOCK, PostOcc<C>::kBlocks)
 k_posterior(const PostParams P)
 	{
 	extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -188,16 +191,18 @@ k_posterior(const PostParams P)
 			float dprev = Z;
 			float bIX = Z, bJX = Z;
 			const int nsteps = LX + nl;
+			int xcPref = h.pad;                       // residue class of the row this lane handles next
 			for (int t = 0; t < nsteps; ++t)
 				{
 				const int i = t - lane;
+				const int xc = xcPref;
+				xcPref = (i >= 0 && i < LX) ? (int) Xc[i] : h.pad;    // row i+1 uses X[i]; consumed next step
 				float Lm = __shfl_up_sync(MB_FULL, outM, 1);
 				float Laiy = __shfl_up_sync(MB_FULL, outAIY, 1);
 				float Lajy = __shfl_up_sync(MB_FULL, outAJY, 1);
 				float Ls = __shfl_up_sync(MB_FULL, outS, 1);
 				if (i >= 0 && i <= LX && lane < nl)
 					{
-					const int xc = i >= 1 ? (int) Xc[i - 1] : h.pad;
 					const float ex = sm.insT[xc];
 					if (lane == 0)
 						{
@@ -305,9 +310,12 @@ k_posterior(const PostParams P)
 			float outM = Z, outIY = Z, outJY = Z;
 			float dprev = Z;
 			const int nsteps = LX + nl - 1;
+			int xcPref = h.pad;
 			for (int u = 0; u < nsteps; ++u)
 				{
 				const int i = LX - u + (nl - 1 - lane);
+				const int xc = xcPref;
+				xcPref = (i >= 2 && i <= LX) ? (int) Xc[i - 1] : h.pad;   // row i-1 uses X[i-1]
 				float Rm = __shfl_down_sync(MB_FULL, outM, 1);
 				float Riy = __shfl_down_sync(MB_FULL, outIY, 1);
 				float Rjy = __shfl_down_sync(MB_FULL, outJY, 1);
@@ -325,9 +333,9 @@ k_posterior(const PostParams P)
 							Rm = e.x; Riy = e.y; Rjy = e.z;
 							}
 						}
-					const int xc = i < LX ? (int) Xc[i] : h.pad;
 					const float ex = sm.insT[xc];
 					const float *mrow = matchT + xc*h.KS;
+					uint32_t cnt = rowcnt[i - 1];             // issued early, consumed after the cell updates
 					const int t = i + lane;
 					const float *src = fms + ((size_t) t*32 + lane)*C;
 					float fmv[C];
@@ -346,7 +354,6 @@ k_posterior(const PostParams P)
 						edgeOut[i] = make_float4(outM, outIY, outJY, 0.0f);
 
 					// posterior (calcposteriorflat.cpp:14-22): candidates arrive with descending column
-					uint32_t cnt = rowcnt[i - 1];
 					const uint32_t cnt0 = cnt;
 					mb200_entry *row = rows + (size_t)(i - 1)*MB_CAP;
 #pragma unroll
