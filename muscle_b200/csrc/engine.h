@@ -41,6 +41,8 @@ struct mb200_ctx
 	uint32_t store_p_lo = 0, store_p_hi = 0;
 	bool store_packed = false;        // entries are packed in store order (entbase ascending, no holes)
 	bool store_tr_valid = false;      // transposed orientation + permutation built
+	bool tr_values_stale = false;     // forward values changed since the transposed copy was refreshed
+	std::vector<uint64_t> h_tr_rowbase;
 	uint64_t store_nnz = 0;
 	uint32_t nnz_per_row_cap = 12;    // entry pool sizing guess (retry with the exact count on overflow)
 	std::vector<uint32_t> h_px, h_py;
@@ -73,4 +75,7 @@ struct mb200_ctx
 	};
 
 int mb_fail(mb200_ctx *ctx, int code, const char *fmt, ...);
+int mb_store_pack_inplace(mb200_ctx *ctx);
+int mb_store_build_transposed(mb200_ctx *ctx);
+int mb_store_refresh_transposed(mb200_ctx *ctx);
 void mb_allpairs_list(uint32_t n, uint32_t p_lo, uint32_t p_hi, std::vector<uint32_t> &px, std::vector<uint32_t> &py);

@@ -176,6 +176,34 @@ class Engine:
 			p_hi = self.nseq*(self.nseq - 1)//2
 		self._ck(self.lib.mb200_consistency_iter(self.h, C.c_uint32(p_lo), C.c_uint32(p_hi)))
 
+	def store_values_torch(self):
+		"""values-only image of the packed store as a CUDA torch tensor (exchange between iterations)"""
+		import torch
+		_, tot = self.store_nnz()
+		# packing may change the layout: ask for the packed image first
+		self._ck(self.lib.mb200_store_pack(self.h, None, None, None, None))
+		v = torch.empty(int(tot), dtype=torch.float32, device="cuda")
+		self._ck(self.lib.mb200_store_values(self.h, C.c_void_p(v.data_ptr()), C.c_uint64(int(tot))))
+		return v
+
+	def store_set_values_torch(self, v, first_entry):
+		self._ck(self.lib.mb200_store_set_values(self.h, C.c_void_p(v.data_ptr()), C.c_uint64(int(first_entry)),
+		  C.c_uint64(int(v.numel()))))
+
+	def store_pack_ptrs(self):
+		"""(d_offsets ptr, n_offsets, d_entries ptr, n_entries) of the packed store"""
+		po, pe = C.c_void_p(), C.c_void_p()
+		no, ne = C.c_uint64(), C.c_uint64()
+		self._ck(self.lib.mb200_store_pack(self.h, C.byref(po), C.byref(no), C.byref(pe), C.byref(ne)))
+		return po.value, no.value, pe.value, ne.value
+
+	def store_load_allpairs(self, p_lo, p_hi, d_offsets_ptr, n_offsets, d_entries_ptr, n_entries):
+		self._ck(self.lib.mb200_store_load_allpairs(self.h, C.c_uint32(p_lo), C.c_uint32(p_hi),
+		  C.c_void_p(d_offsets_ptr), C.c_uint64(n_offsets), C.c_void_p(d_entries_ptr), C.c_uint64(n_entries)))
+		n = self.nseq
+		px, py = np.triu_indices(n, 1)
+		self._pairs = (px[p_lo:p_hi].astype(np.uint32), py[p_lo:p_hi].astype(np.uint32))
+
 	# ---- posterior decoding
 	def align_pairs(self, store_pairs):
 		sp = np.ascontiguousarray(store_pairs, np.uint32)

@@ -1,0 +1,137 @@
+"""GPU parity of the consistency (relax) iteration, the packed store and the posterior decoding
+kernels against the CPU oracle.  The relax arithmetic is fp32 mul/add in the reference's order, so
+given IDENTICAL inputs the update is compared bit-exact; inputs come from the GPU posterior stage
+(expf differs from glibc by <= 2 ulp), therefore the oracle is fed the GPU store itself."""
+import os
+import numpy as np
+import pytest
+from conftest import GOLDEN
+from muscle_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _pairs(n):
+	return [(i, j) for i in range(n) for j in range(i + 1, n)]
+
+
+def test_export_all_matches_export_pair(engine):
+	seqs = synth.make_family(9, 70, 15, seed=41)
+	engine.set_seqs(seqs)
+	engine.posteriors_allpairs()
+	nnz, tot = engine.store_nnz()
+	singles = [engine.export_pair(k, int(nnz[k])) for k in range(len(nnz))]
+	offs, ents = engine.export_all()
+	assert sum(len(e) for e in ents) == tot
+	for k in range(len(nnz)):
+		assert (offs[k] == singles[k][0]).all() and ents[k].tobytes() == singles[k][1].tobytes()
+		# columns ascending inside every row (MySparseMx invariant)
+		for i in range(len(offs[k]) - 1):
+			c = ents[k]["col"][offs[k][i]:offs[k][i + 1]]
+			assert (np.diff(c.astype(np.int64)) > 0).all()
+
+
+@pytest.mark.parametrize("n,L,seed", [(3, 50, 1), (8, 70, 2), (20, 120, 3)])
+def test_consistency_bitexact_vs_oracle(engine, oracle, n, L, seed):
+	seqs = synth.make_family(n, L, L//5, seed=seed)
+	lens = [len(s) for s in seqs]
+	engine.set_seqs(seqs)
+	engine.posteriors_allpairs()
+	offs, ents = engine.export_all()
+	for it in range(2):
+		want = [oracle.conspair(lens, x, y, offs, ents) for (x, y) in _pairs(n)]
+		engine.consistency_iter()
+		offs2, got = engine.export_all()
+		for p in range(len(want)):
+			assert (offs2[p] == offs[p]).all()
+			assert got[p].tobytes() == want[p].tobytes(), "iter %d pair %d" % (it, p)
+		ents = got
+
+
+def test_consistency_golden_family8(engine):
+	"""against the compiled reference's own output (tests/golden/family8.npz): same pattern,
+	values within 1e-6 (the inputs differ by the expf ulp)."""
+	z = np.load(os.path.join(GOLDEN, "family8.npz"))
+	seqs = [z["seq%d" % i].tobytes() for i in range(int(z["n"]))]
+	engine.set_seqs(seqs)
+	engine.posteriors_allpairs()
+	for it in (1, 2):
+		engine.consistency_iter()
+		offs, ents = engine.export_all()
+		for p in range(len(offs)):
+			g = z["ent%d_%d" % (it, p)]
+			if len(g) == len(ents[p]) and (g["col"] == ents[p]["col"]).all():
+				assert np.abs(g["p"] - ents[p]["p"]).max(initial=0) <= 1e-6
+
+
+def test_consistency_partial_range_and_values_exchange(engine, oracle):
+	"""sharded update: two half-range calls on copies == one full call (what two ranks would do)"""
+	import torch
+	seqs = synth.make_family(7, 60, 10, seed=5)
+	n = len(seqs)
+	engine.set_seqs(seqs)
+	engine.posteriors_allpairs()
+	offs, ents0 = engine.export_all()
+	lens = [len(s) for s in seqs]
+	want = [oracle.conspair(lens, x, y, offs, ents0) for (x, y) in _pairs(n)]
+	npairs = n*(n - 1)//2
+	half = npairs//2
+	# rank A updates [0,half); grab its new values, then restore and let "rank B" update [half,npairs)
+	nnz, tot = engine.store_nnz()
+	base = np.concatenate([[0], np.cumsum(nnz)]).astype(np.int64)
+	engine.consistency_iter(0, half)
+	va = engine.store_values_torch()
+	engine.posteriors_allpairs()
+	engine.consistency_iter(half, npairs)
+	# exchange: bring rank A's values for its range
+	engine.store_set_values_torch(va[:base[half]], 0)
+	_, got = engine.export_all()
+	for p in range(npairs):
+		assert got[p].tobytes() == want[p].tobytes(), p
+
+
+def test_align_pairs_vs_oracle(engine, oracle):
+	seqs = synth.make_family(6, 90, 25, seed=13) + ["ACDEFGHIKLMNPQRSTVWY"*20]     # LY=400 > 256 threads
+	engine.set_seqs(seqs)
+	engine.posteriors_allpairs()
+	offs, ents = engine.export_all()
+	n = len(seqs)
+	pairs = _pairs(n)
+	sel = list(range(len(pairs)))
+	scores, paths = engine.align_pairs(sel)
+	for k in sel:
+		x, y = pairs[k]
+		dense = np.zeros((len(seqs[x]), len(seqs[y])), np.float32)
+		for i in range(len(seqs[x])):
+			for e in range(offs[k][i], offs[k][i + 1]):
+				dense[i, ents[k]["col"][e]] = ents[k]["p"][e]
+		s, path = oracle.calcaln(dense)
+		assert np.float32(s) == scores[k] and path == paths[k], k
+
+
+def test_align_groups_vs_oracle(engine, oracle):
+	seqs = synth.make_family(7, 70, 10, seed=21)
+	lens = [len(s) for s in seqs]
+	engine.set_seqs(seqs)
+	engine.posteriors_allpairs()
+	engine.consistency_iter()
+	offs, ents = engine.export_all()
+	c1 = max(len(seqs[0]), len(seqs[1]) + 2, len(seqs[5]) + 1)
+	c2 = max(len(seqs[2]), len(seqs[3]) + 1, len(seqs[4]))
+	rows1 = [seqs[0] + "-"*(c1 - len(seqs[0])), "--" + seqs[1] + "-"*(c1 - 2 - len(seqs[1])), "-" + seqs[5] + "-"*(c1 - 1 - len(seqs[5]))]
+	rows2 = [seqs[2] + "-"*(c2 - len(seqs[2])), "-" + seqs[3] + "-"*(c2 - 1 - len(seqs[3])), seqs[4] + "-"*(c2 - len(seqs[4]))]
+
+	def p2c(row):
+		return np.array([c for c, ch in enumerate(row) if ch != "-"], np.uint32)
+	ids1, ids2 = [0, 1, 5], [2, 3, 4]
+	want = oracle.buildpost(lens, ids1, [p2c(r) for r in rows1], c1, ids2, [p2c(r) for r in rows2], c2, offs, ents)
+	score, path, post = engine.align_groups(ids1, [p2c(r) for r in rows1], c1, ids2, [p2c(r) for r in rows2], c2, want_post=True)
+	assert post.tobytes() == want.tobytes()
+	s, pth = oracle.calcaln(want)
+	assert np.float32(s) == np.float32(score) and pth == path
+	# the transposed orientation (group ids reversed: stored pair is (t,s))
+	want2 = oracle.buildpost(lens, ids2, [p2c(r) for r in rows2], c2, ids1, [p2c(r) for r in rows1], c1, offs, ents)
+	score2, path2, post2 = engine.align_groups(ids2, [p2c(r) for r in rows2], c2, ids1, [p2c(r) for r in rows1], c1, want_post=True)
+	assert post2.tobytes() == want2.tobytes()
+	s2, pth2 = oracle.calcaln(want2)
+	assert np.float32(s2) == np.float32(score2) and pth2 == path2
