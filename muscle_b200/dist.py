@@ -1,0 +1,109 @@
+"""Multi-GPU plumbing for the MPCFlat pair engine.
+
+One process per GPU (torchrun), NCCL over NVLink for the two exchange steps the path really has:
+  1. after the posterior stage: all-gather of the variable-length sparse blocks (row offsets and
+     {P,col} entries of each rank's contiguous pair range), so every rank holds the full store;
+  2. after each consistency iteration: all-gather of the updated VALUES only (the pattern is
+     invariant, mysparsemx.cpp:87-113).
+The posterior stage itself needs no collective: pairs are independent and are sharded in
+contiguous, cell-balanced ranges of the reference's row-major pair order, which makes the
+all-gather-v a plain concatenation in rank order.
+All functions take torch tensors and a process group, so the host logic is testable on CPU with
+the gloo backend (tests/test_dist_cpu.py).
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def shard_ranges(lens, world):
+	"""Contiguous ranges [lo,hi) of the row-major (i<j) pair list with ~equal DP cells per rank.
+	-> (ranges, cells_per_rank, total_cells)"""
+	L = np.asarray(lens, np.float64)
+	n = len(L)
+	iu, ju = np.triu_indices(n, 1)
+	cost = np.cumsum(L[iu]*L[ju])
+	total = float(cost[-1])
+	cuts = [0]
+	for r in range(1, world):
+		cuts.append(int(np.searchsorted(cost, total*r/world)))
+	cuts.append(len(iu))
+	for r in range(1, len(cuts)):
+		cuts[r] = max(cuts[r], cuts[r - 1])
+	cells = []
+	for r in range(world):
+		lo, hi = cuts[r], cuts[r + 1]
+		cells.append(float(cost[hi - 1] - (cost[lo - 1] if lo > 0 else 0.0)) if hi > lo else 0.0)
+	return [(cuts[r], cuts[r + 1]) for r in range(world)], cells, total
+
+
+def allgather_v(t, group=None):
+	"""all-gather of 1-D tensors of different lengths -> (concatenation in rank order, sizes).
+	Sizes are exchanged first; payloads are padded to the longest shard for one all_gather."""
+	world = dist.get_world_size(group)
+	n = torch.tensor([t.numel()], dtype=torch.int64, device=t.device)
+	sizes = [torch.zeros_like(n) for _ in range(world)]
+	dist.all_gather(sizes, n, group=group)
+	sizes = [int(s.item()) for s in sizes]
+	mx = max(sizes)
+	pad = torch.zeros(mx, dtype=t.dtype, device=t.device)
+	pad[:t.numel()] = t
+	parts = [torch.empty(mx, dtype=t.dtype, device=t.device) for _ in range(world)]
+	dist.all_gather(parts, pad, group=group)
+	return torch.cat([parts[r][:sizes[r]] for r in range(world)]), sizes
+
+
+class _DevView:
+	"""zero-copy torch view of library-owned device memory (__cuda_array_interface__)"""
+
+	def __init__(self, ptr, nbytes):
+		self.__cuda_array_interface__ = {"shape": (int(nbytes),), "typestr": "|u1", "data": (int(ptr), False),
+		  "version": 2, "strides": None}
+
+
+def device_view(ptr, nbytes, device):
+	if nbytes == 0:
+		return torch.empty(0, dtype=torch.uint8, device=device)
+	return torch.as_tensor(_DevView(ptr, nbytes), device=device)
+
+
+def gather_store(engine, group=None):
+	"""Exchange step 1: every rank contributes the packed image of its pair range; afterwards every
+	rank's engine holds the full all-pairs store.  Returns bytes received per rank."""
+	dev = torch.device("cuda", torch.cuda.current_device())
+	po, no, pe, ne = engine.store_pack_ptrs()
+	offs = device_view(po, no*4, dev).view(torch.int32)
+	ents = device_view(pe, ne*8, dev).view(torch.int64)
+	all_offs, _ = allgather_v(offs, group)
+	all_ents, _ = allgather_v(ents, group)
+	n = engine.nseq
+	engine.store_load_allpairs(0, n*(n - 1)//2, all_offs.data_ptr(), all_offs.numel(), all_ents.data_ptr(), all_ents.numel())
+	return all_offs.numel()*4 + all_ents.numel()*8
+
+
+def gather_values(engine, entry_ranges, rank, group=None):
+	"""Exchange step 2: after a sharded consistency iteration each rank owns new values for the
+	entries of its pair range [entry_ranges[rank]); all-gather them and install the peers' parts."""
+	v = engine.store_values_torch()
+	lo, hi = entry_ranges[rank]
+	mine = v[lo:hi].contiguous()
+	allv, sizes = allgather_v(mine, group)
+	assert allv.numel() == v.numel(), (allv.numel(), v.numel())
+	engine.store_set_values_torch(allv, 0)
+	return allv.numel()*4
+
+
+def gather_ea(ea_local, ranges, n, group=None):
+	"""EA of every pair on every rank (N*N floats after symmetrisation), as the guide tree needs."""
+	t = torch.as_tensor(np.ascontiguousarray(ea_local, np.float32))
+	if dist.is_initialized() and dist.get_world_size(group) > 1:
+		if dist.get_backend(group) == "nccl":
+			t = t.cuda()
+		t, _ = allgather_v(t, group)
+		t = t.cpu()
+	ea = t.numpy()
+	m = np.zeros((n, n), np.float32)
+	iu = np.triu_indices(n, 1)
+	m[iu] = ea
+	m.T[iu] = ea
+	return m

@@ -15,3 +15,10 @@ for it in range(3):
 	s = e.stats()
 	print("%s iter %d: wall %.3f s, kernel %.1f ms, total %.1f ms -> %.2f Gcells/s (kernel), nnz %d, EA mean %.3f" %
 	  (name, it, t1 - t0, s["last_kernel_ms"], s["last_total_ms"], cells/s["last_kernel_ms"]/1e6, e.store_nnz()[1], ea.mean()))
+if len(sys.argv) > 2 and sys.argv[2] == "relax":
+	for it in range(2):
+		t0 = time.time(); e.consistency_iter(); t1 = time.time()
+		s = e.stats()
+		n = len(seqs)
+		triples = n*(n - 1)//2*(n - 2)
+		print("%s consistency iter %d: wall %.3f s, kernel %.1f ms -> %.3g (XY,Z) triples/s" % (name, it, t1 - t0, s["last_kernel_ms"], triples/(s["last_kernel_ms"]*1e-3)))
