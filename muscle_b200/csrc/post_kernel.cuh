@@ -103,7 +103,10 @@ __device__ __forceinline__ void bwd_cells(const MbHmm &h, const LogAdd &la, cons
 	}
 
 // resident CTAs per SM the register budget is tuned for (4 warps each)
-template <int C> struct PostOcc { static constexpr int kBlocks = C <= 5 ? 5 : (C <= 8 ? 4 : 3); };
+#ifndef MB_OCC_EXPR
+#define MB_OCC_EXPR (C <= 8 ? 5 : (C <= 12 ? 4 : 3))     // measured on C3: +5 % over 3 CTAs/SM, spills <= 120 B
+#endif
+template <int C> struct PostOcc { static constexpr int kBlocks = MB_OCC_EXPR; };
 
 template <int C>
 __global__ void __launch_bounds__(32*MB_WARPS_PER_BLOCK, PostOcc<C>::kBlocks)

@@ -93,10 +93,12 @@ def gather_values(engine, entry_ranges, rank, group=None):
 	return allv.numel()*4
 
 
-def gather_ea(ea_local, ranges, n, group=None):
+def gather_ea(ea_local, ranges, n, group=None, distributed=None):
 	"""EA of every pair on every rank (N*N floats after symmetrisation), as the guide tree needs."""
 	t = torch.as_tensor(np.ascontiguousarray(ea_local, np.float32))
-	if dist.is_initialized() and dist.get_world_size(group) > 1:
+	if distributed is None:
+		distributed = dist.is_initialized() and dist.get_world_size(group) > 1
+	if distributed:
 		if dist.get_backend(group) == "nccl":
 			t = t.cuda()
 		t, _ = allgather_v(t, group)

@@ -8,7 +8,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libmuscle_b200.so")
+LIB_PATH = os.environ.get("MB200_LIB", os.path.join(HERE, "libmuscle_b200.so"))   # MB200_LIB: tuning builds only
 
 ENTRY = np.dtype([("p", "<f4"), ("col", "<u4")])
 

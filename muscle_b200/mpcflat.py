@@ -73,7 +73,7 @@ class MPCFlat:
 		ea = self.engine.posteriors_allpairs(lo, hi) if hi > lo else np.zeros(0, np.float32)
 		if self._world > 1:
 			mdist.gather_store(self.engine, self.group)
-		m = mdist.gather_ea(ea, self._ranges, n, self.group)
+		m = mdist.gather_ea(ea, self._ranges, n, self.group, distributed=self._world > 1)
 		iu = np.triu_indices(n, 1)
 		self.m_DistMx[iu] = m[iu]
 		self.m_DistMx.T[iu] = m[iu]
