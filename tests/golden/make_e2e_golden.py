@@ -1,0 +1,39 @@
+"""End-to-end golden MSAs: run the COMPILED, UNMODIFIED reference CLI (oracle/_ref/muscle, strict-IEEE
+build) on seeded synthetic FASTA inputs and commit input + output under tests/golden/e2e/.
+    python tests/golden/make_e2e_golden.py
+"""
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from muscle_b200 import synth   # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden", "e2e")
+CLI = os.path.join(ROOT, "oracle", "_ref", "muscle")
+
+SETS = {
+	"fam12": dict(n=12, mean=80, sd=12, seed=101),
+	"fam30": dict(n=30, mean=120, sd=25, seed=102, dupes=[(3, 17)]),
+	"fam6_long": dict(n=6, mean=600, sd=60, seed=103),
+}
+
+
+def main():
+	os.makedirs(OUT, exist_ok=True)
+	for name, cfg in SETS.items():
+		seqs = synth.make_family(cfg["n"], cfg["mean"], cfg["sd"], cfg["seed"])
+		for a, b in cfg.get("dupes", []):
+			seqs[b] = seqs[a]                  # exercises Derep / InsertDupes (mpcflat.cpp:290-294,421)
+		fa = os.path.join(OUT, name + ".fa")
+		with open(fa, "w") as f:
+			for i, s in enumerate(seqs):
+				f.write(">s%d\n%s\n" % (i, s))
+		out = os.path.join(OUT, name + ".ref.afa")
+		subprocess.run([CLI, "-align", fa, "-output", out, "-quiet"], check=True)
+		print(name, "->", out)
+
+
+if __name__ == "__main__":
+	main()
