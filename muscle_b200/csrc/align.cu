@@ -323,19 +323,20 @@ int mb200_align_groups(mb200_ctx *ctx, uint32_t na, const uint32_t *ids_a, const
 	const size_t post_bytes = (size_t) cols_a*cols_b*sizeof(float);
 	const size_t tb_bytes = (size_t)(cols_a + 1)*(cols_b + 1);
 	const size_t path_bytes = (size_t) cols_a + cols_b + 16;
-	size_t need = post_bytes + ((tb_bytes + 15)/16)*16 + ((path_bytes + 15)/16)*16 + 64 + sizeof(AlnProblem)
-	  + ((c2p.size()*4 + 15)/16)*16 + ((btot*4 + 15)/16)*16 + nb*8 + (na + nb)*4 + 64;
+	auto al16 = [](size_t b) { return (b + 15)/16*16; };
+	const size_t need = al16(post_bytes) + al16(tb_bytes) + al16(path_bytes) + 16 + al16(sizeof(AlnProblem))
+	  + al16(c2p.size()*4) + al16(btot*4) + al16(nb*8) + al16(na*4) + al16(nb*4) + 64;
 	ENSURE(ctx->d_tmp, need);
-	char *base = (char *) ctx->d_tmp.p;
-	float *d_post = (float *) base;                  base += post_bytes;
-	char *d_tb = base;                               base += ((tb_bytes + 15)/16)*16;
-	char *d_path = base;                             base += ((path_bytes + 15)/16)*16;
+	char *base = (char *) ctx->d_tmp.p;          // cudaMalloc base is 256-byte aligned; every slice 16-byte aligned
+	float *d_post = (float *) base;                  base += al16(post_bytes);
+	char *d_tb = base;                               base += al16(tb_bytes);
+	char *d_path = base;                             base += al16(path_bytes);
 	float *d_score = (float *) base;                 base += 16;
-	AlnProblem *d_prob = (AlnProblem *) base;        base += ((sizeof(AlnProblem) + 15)/16)*16;
-	int32_t *d_c2p = (int32_t *) base;               base += ((c2p.size()*4 + 15)/16)*16;
-	uint32_t *d_p2cb = (uint32_t *) base;            base += ((btot*4 + 15)/16)*16;
-	uint64_t *d_boff = (uint64_t *) base;            base += nb*8;
-	uint32_t *d_ida = (uint32_t *) base;             base += na*4;
+	AlnProblem *d_prob = (AlnProblem *) base;        base += al16(sizeof(AlnProblem));
+	int32_t *d_c2p = (int32_t *) base;               base += al16(c2p.size()*4);
+	uint32_t *d_p2cb = (uint32_t *) base;            base += al16(btot*4);
+	uint64_t *d_boff = (uint64_t *) base;            base += al16(nb*8);
+	uint32_t *d_ida = (uint32_t *) base;             base += al16(na*4);
 	uint32_t *d_idb = (uint32_t *) base;
 	CU(cudaMemsetAsync(d_post, 0, post_bytes, st));
 	CU(cudaMemcpyAsync(d_c2p, c2p.data(), c2p.size()*4, cudaMemcpyHostToDevice, st));
