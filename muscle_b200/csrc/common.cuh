@@ -84,6 +84,7 @@ struct PostParams
 	uint8_t     *rowcnt;  size_t rowcnt_stride;  // bytes
 	uint32_t     lxmax;                          // rows the scratch was sized for
 	uint32_t     fm_rows;                        // (lxmax+33): steps per strip slot in fm
+	uint32_t     cmax;                           // k_posterior_sm: columns per lane the smem state is sized for
 	// outputs
 	uint32_t       *rowoff;         // concatenated, pair k at rowbase[k], LX+1 entries
 	const uint64_t *rowbase;

@@ -72,6 +72,7 @@ struct mb200_ctx
 	cudaEvent_t aux_done[kStreams] = {};
 	DevBuf d_dbg;
 	int debug_force_c = 0;
+	bool use_sm_kernel = true;        // k_posterior_sm (state in smem) vs k_posterior<C> (state in registers)
 	};
 
 int mb_fail(mb200_ctx *ctx, int code, const char *fmt, ...);
