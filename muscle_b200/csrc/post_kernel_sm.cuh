@@ -17,6 +17,14 @@
 #include "common.cuh"
 
 #define MB_SM_ARRAYS 6            // S/old, M, IX, JX, ycode, eY
+#ifndef MB_SM_BLOCKS
+#define MB_SM_BLOCKS 5            // resident CTAs/SM the register budget is tuned for (measured best of 4/5/6/8)
+#endif
+#ifndef MB_SM_UNROLL
+#define MB_SM_UNROLL 1            // measured on C3: unroll 1: 51.7, 2: 51.2, 4: 37.7 Gcells/s (I-cache)
+#endif
+#define MB_PRAGMA(x) _Pragma(#x)
+#define MB_UNROLL(n) MB_PRAGMA(unroll n)
 
 struct PostSmemHdr
 	{
@@ -24,7 +32,7 @@ struct PostSmemHdr
 	float  insT[MB_MAX_K];
 	};
 
-__global__ void __launch_bounds__(32*MB_WARPS_PER_BLOCK)
+__global__ void __launch_bounds__(32*MB_WARPS_PER_BLOCK, MB_SM_BLOCKS)
 k_posterior_sm(const PostParams P)
 	{
 	extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -156,7 +164,7 @@ k_posterior_sm(const PostParams P)
 					const bool cap = last && i == LX && lane == lcl;
 					float *dst = fms + (size_t) t*W + lane;
 					const bool dump = P.dbg_fwd != nullptr && i >= 1;
-#pragma unroll 2
+MB_UNROLL(MB_SM_UNROLL)
 					for (int c = 0; c < C; ++c)
 						{
 						const int o = c*32 + lane;
@@ -270,7 +278,7 @@ k_posterior_sm(const PostParams P)
 					const bool inj = last && i == LX && lane == lcl;
 					const bool dump = P.dbg_bwd != nullptr;
 					float fmNext = src[(C - 1)*32];
-#pragma unroll 2
+MB_UNROLL(MB_SM_UNROLL)
 					for (int c = C - 1; c >= 0; --c)
 						{
 						const int o = c*32 + lane;
