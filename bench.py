@@ -287,7 +287,7 @@ def main():
 		    "what": "mb200_set_seqs(host bytes) + mb200_posteriors_allpairs -> EA on host; sparse store stays in HBM for the next stage"},
 		  "gpu_launches": int(launches),
 		  "clocks": clocks,
-		  "roofline": {"bound": "hbm", "kernel": "k_posterior<C>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+		  "roofline": {"bound": "hbm", "kernel": "k_posterior_sm", "achieved": achieved, "peak": peak, "unit": "GB/s",
 		    "frac": achieved/peak, "traffic": traffic, "peak_source": peak_src,
 		    "algorithmic_bytes_per_cell": ALGO_BYTES_PER_CELL,
 		    "kernel_ms_per_step": kern_ms/steps,
