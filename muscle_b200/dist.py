@@ -77,6 +77,8 @@ def gather_store(engine, group=None):
 	all_offs, _ = allgather_v(offs, group)
 	all_ents, _ = allgather_v(ents, group)
 	n = engine.nseq
+	# the library reads these buffers on its own (non-blocking) stream: finish the collective first
+	torch.cuda.current_stream().synchronize()
 	engine.store_load_allpairs(0, n*(n - 1)//2, all_offs.data_ptr(), all_offs.numel(), all_ents.data_ptr(), all_ents.numel())
 	return all_offs.numel()*4 + all_ents.numel()*8
 
@@ -89,6 +91,7 @@ def gather_values(engine, entry_ranges, rank, group=None):
 	mine = v[lo:hi].contiguous()
 	allv, sizes = allgather_v(mine, group)
 	assert allv.numel() == v.numel(), (allv.numel(), v.numel())
+	torch.cuda.current_stream().synchronize()        # see gather_store
 	engine.store_set_values_torch(allv, 0)
 	return allv.numel()*4
 

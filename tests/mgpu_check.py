@@ -40,10 +40,14 @@ def main():
 	soffs, sents0 = S.engine.export_all()
 	S.Consistency()
 	_, sents2 = S.engine.export_all()
-	ok = np.array_equal(ea, S.m_DistMx)
-	for p in range(len(offs)):
-		ok = ok and np.array_equal(offs[p], soffs[p]) and ents0[p].tobytes() == sents0[p].tobytes() \
-		  and ents2[p].tobytes() == sents2[p].tobytes()
+	ok_ea = np.array_equal(ea, S.m_DistMx)
+	bad_off = [p for p in range(len(offs)) if not np.array_equal(offs[p], soffs[p])]
+	bad0 = [p for p in range(len(offs)) if ents0[p].tobytes() != sents0[p].tobytes()]
+	bad2 = [p for p in range(len(offs)) if ents2[p].tobytes() != sents2[p].tobytes()]
+	ok = ok_ea and not bad_off and not bad0 and not bad2
+	if not ok:
+		print("rank", rank, "ranges", M._ranges, "ea", ok_ea, "bad_off", bad_off[:5], len(bad_off), "bad0", bad0[:5], len(bad0),
+		  "bad2", bad2[:5], len(bad2), flush=True)
 	flag = torch.tensor([1 if ok else 0], device="cuda")
 	dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 	if rank == 0:

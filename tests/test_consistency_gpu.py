@@ -135,3 +135,55 @@ def test_align_groups_vs_oracle(engine, oracle):
 	assert post2.tobytes() == want2.tobytes()
 	s2, pth2 = oracle.calcaln(want2)
 	assert np.float32(s2) == np.float32(score2) and pth2 == path2
+
+
+@pytest.mark.parametrize("world", [3, 8])
+def test_virtual_ranks_pipeline(tables, oracle, world):
+	"""the sharded pipeline with `world` virtual ranks on one GPU (no NCCL): every rank computes its
+	pair range, the packed images are concatenated as the all-gather would, every rank loads the full
+	store, runs its range of the consistency iteration, values are exchanged -- and all ranks must end
+	bit-identical to a single-engine run (exercises middle ranges of every library call)."""
+	import torch
+	from muscle_b200.engine import Engine
+	from muscle_b200 import dist as mdist
+	seqs = synth.make_family(26, 90, 25, seed=9)
+	n = len(seqs)
+	lens = [len(s) for s in seqs]
+	npairs = n*(n - 1)//2
+	ranges, _, _ = mdist.shard_ranges(lens, world)
+	single = Engine(0); single.set_hmm(tables); single.set_seqs(seqs)
+	ea_s = single.posteriors_allpairs()
+	single.consistency_iter(); single.consistency_iter()
+	offs_s, ents_s = single.export_all()
+	engines = []
+	for r in range(world):
+		e = Engine(0); e.set_hmm(tables); e.set_seqs(seqs)
+		engines.append(e)
+	dev = torch.device("cuda", 0)
+	img_off, img_ent, eas = [], [], []
+	for r, (lo, hi) in enumerate(ranges):
+		eas.append(engines[r].posteriors_allpairs(lo, hi))
+		po, no, pe, ne = engines[r].store_pack_ptrs()
+		img_off.append(mdist.device_view(po, no*4, dev).view(torch.int32).clone())
+		img_ent.append(mdist.device_view(pe, ne*8, dev).view(torch.int64).clone())
+	assert np.array_equal(np.concatenate(eas), ea_s)
+	all_off, all_ent = torch.cat(img_off), torch.cat(img_ent)
+	for e in engines:
+		e.store_load_allpairs(0, npairs, all_off.data_ptr(), all_off.numel(), all_ent.data_ptr(), all_ent.numel())
+	nnz, _ = engines[0].store_nnz()
+	base = np.concatenate([[0], np.cumsum(nnz.astype(np.int64))])
+	for it in range(2):
+		parts = []
+		for r, (lo, hi) in enumerate(ranges):
+			engines[r].consistency_iter(lo, hi)
+			v = engines[r].store_values_torch()
+			parts.append(v[int(base[lo]):int(base[hi])].clone())
+		allv = torch.cat(parts)
+		for e in engines:
+			e.store_set_values_torch(allv, 0)
+	for r, e in enumerate(engines):
+		offs, ents = e.export_all()
+		for p in range(npairs):
+			assert np.array_equal(offs[p], offs_s[p]) and ents[p].tobytes() == ents_s[p].tobytes(), (r, p)
+		e.close()
+	single.close()
