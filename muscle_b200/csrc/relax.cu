@@ -14,6 +14,7 @@
 // bit-identical (verified against the oracle).  Relax is a sparse-sparse contraction (about 7
 // non-zeros per row, 2 % density): tensor cores do not apply (DESIGN.md "relax is not a GEMM").
 #include "engine.h"
+#include <algorithm>
 #include <cstdlib>
 #include <cstring>
 
