@@ -1,0 +1,230 @@
+// integration/pairlist_b200_shim.cpp -- reference-side binding of the PAIR-LIST callers of the hot
+// path: everything in `muscle -super5` that calls CalcPost on a
+// list of sequence pairs outside MPCFlat.  Replaced at link time:
+//   PProg::GetPostPairsAlignedFlat  (getpostpairsalignedflat.cpp:5-98)  -> one mb200_posteriors batch
+//   CalcEADistMx                    (eadistmx.cpp:7-70)                 -> one mb200_posteriors batch
+//   AlignPairFlat_SparsePost / AlignPairFlat (alignpairflat.cpp:3-31)   -> 1-pair batch (+ mb200_align_pairs)
+// Sequences are resolved through the reference's own global label registry
+// (GetGlobalInputSeqByLabel, globalinputms.cpp:125-143) and handed to the library by index.
+// A context of its own is used so that an MPCFlat store (mpcflat_b200_shim.cpp) is never disturbed;
+// the per-pair entry points are serialised by a mutex (UClust/EACluster call them from OpenMP loops).
+#include "muscle.h"
+#include "pprog.h"
+#include "pairhmm.h"
+#include "../include/muscle_b200.h"
+#include <mutex>
+#include <unordered_map>
+
+static mb200_ctx *g_PairCtx = 0;
+static std::mutex g_PairMutex;
+
+static void CheckP(int rc, const char *What)
+	{
+	if (rc != MB200_OK)
+		Die("libmuscle_b200 %s failed (%d): %s", What, rc, mb200_last_error(g_PairCtx));
+	}
+
+static void EnsurePairCtx()
+	{
+	if (g_PairCtx == 0)
+		{
+		int Device = 0;
+		const char *s = getenv("MB200_DEVICE");
+		if (s != 0)
+			Device = atoi(s);
+		int rc = mb200_create(Device, &g_PairCtx);
+		if (rc != MB200_OK)
+			Die("libmuscle_b200 mb200_create failed (%d): %s", rc, mb200_last_error(0));
+		}
+	CheckP(mb200_set_hmm(g_PairCtx, PairHMM::m_StartScore, &PairHMM::m_TransScore[0][0],
+	  PairHMM::m_InsScore, &PairHMM::m_MatchScore[0][0], MIN_SPARSE_SCORE), "mb200_set_hmm");
+	}
+
+// Upload the distinct sequences named by the two label lists and run the posterior stage on the
+// pair list.  EAs[k] = what CalcAlnFlat(Post)/min(L1,L2) gives in the reference (the max-sum DP
+// value of CalcAlnFlat and CalcAlnScoreFlat is the same number).
+static void RunPairList(const vector<string> &Labels1, const vector<string> &Labels2, vector<float> &EAs)
+	{
+	const uint PairCount = SIZE(Labels1);
+	asserta(SIZE(Labels2) == PairCount && PairCount > 0);
+	unordered_map<string, uint> LabelToId;
+	vector<byte> Bytes;
+	vector<uint64_t> Offsets(1, 0);
+	vector<uint> PX(PairCount), PY(PairCount);
+	for (uint k = 0; k < PairCount; ++k)
+		{
+		for (int side = 0; side < 2; ++side)
+			{
+			const string &Label = side == 0 ? Labels1[k] : Labels2[k];
+			unordered_map<string, uint>::const_iterator it = LabelToId.find(Label);
+			uint Id;
+			if (it == LabelToId.end())
+				{
+				Id = SIZE(LabelToId);
+				LabelToId[Label] = Id;
+				const Sequence &Seq = GetGlobalInputSeqByLabel(Label);
+				const byte *B = Seq.GetBytePtr();
+				Bytes.insert(Bytes.end(), B, B + Seq.GetLength());
+				Offsets.push_back(Bytes.size());
+				}
+			else
+				Id = it->second;
+			(side == 0 ? PX : PY)[k] = Id;
+			}
+		}
+	CheckP(mb200_set_seqs(g_PairCtx, SIZE(LabelToId), Bytes.data(), Offsets.data()), "mb200_set_seqs");
+	EAs.resize(PairCount);
+	CheckP(mb200_posteriors(g_PairCtx, PairCount, PX.data(), PY.data(), MB200_POST_DEFAULT, EAs.data()),
+	  "mb200_posteriors");
+	}
+
+// fill host MySparseMx objects (MySparseMx::FromPost layout) for store pairs [0,PairCount)
+static void ExportSparse(const vector<string> &Labels1, vector<MySparseMx *> &SparsePosts)
+	{
+	const uint PairCount = SIZE(SparsePosts);
+	vector<uint> Nnz(PairCount);
+	uint64_t Total = 0;
+	CheckP(mb200_store_nnz(g_PairCtx, Nnz.data(), &Total), "mb200_store_nnz");
+	uint64_t Rows = 0;
+	vector<uint> LX(PairCount);
+	for (uint k = 0; k < PairCount; ++k)
+		{
+		LX[k] = GetSeqLengthByGlobalLabel(Labels1[k]);
+		Rows += LX[k] + 1;
+		}
+	vector<uint> Offs(Rows);
+	vector<mb200_entry> Ents(Total + 1);
+	CheckP(mb200_export_all(g_PairCtx, Offs.data(), Ents.data()), "mb200_export_all");
+	uint64_t r = 0, e = 0;
+	for (uint k = 0; k < PairCount; ++k)
+		{
+		MySparseMx *S = SparsePosts[k];
+		S->AllocLX(LX[k]);
+		memcpy(S->m_Offsets, Offs.data() + r, (LX[k] + 1)*sizeof(uint));
+		S->m_VecSize = Nnz[k];
+		S->AllocVec(Nnz[k]);
+		memcpy(S->m_ValueVec, Ents.data() + e, size_t(Nnz[k])*8);
+		r += LX[k] + 1;
+		e += Nnz[k];
+		}
+	}
+
+float PProg::GetPostPairsAlignedFlat(const string &aProgressStr,
+  const MultiSequence &MSA1, const MultiSequence &MSA2,
+  const vector<uint> &SeqIndexes1, const vector<uint> &SeqIndexes2,
+  vector<MySparseMx *> &SparsePosts)
+	{
+	const uint PairCount = SIZE(SeqIndexes1);
+	asserta(SIZE(SeqIndexes2) == PairCount);
+	asserta(SparsePosts.empty());
+	std::lock_guard<std::mutex> Guard(g_PairMutex);
+	EnsurePairCtx();
+	ProgressStep(0, 2, "%s [%u x %u, %u pairs] (B200)", aProgressStr.substr(0, 20).c_str(),
+	  min(MSA1.GetSeqCount(), MSA2.GetSeqCount()), max(MSA1.GetSeqCount(), MSA2.GetSeqCount()), PairCount);
+	vector<string> Labels1, Labels2;
+	for (uint k = 0; k < PairCount; ++k)
+		{
+		Labels1.push_back(MSA1.GetLabelStr(SeqIndexes1[k]));
+		Labels2.push_back(MSA2.GetLabelStr(SeqIndexes2[k]));
+		}
+	vector<float> EAs;
+	RunPairList(Labels1, Labels2, EAs);
+	SparsePosts.resize(PairCount);
+	for (uint k = 0; k < PairCount; ++k)
+		{
+		MySparseMx *S = new MySparseMx;
+		S->m_LX = GetSeqLengthByGlobalLabel(Labels1[k]);
+		S->m_LY = GetSeqLengthByGlobalLabel(Labels2[k]);
+		SparsePosts[k] = S;
+		}
+	ExportSparse(Labels1, SparsePosts);
+	float SumEA = 0;
+	for (uint k = 0; k < PairCount; ++k)
+		SumEA += EAs[k];
+	ProgressStep(1, 2, "%s [%u pairs] (B200)", aProgressStr.substr(0, 20).c_str(), PairCount);
+	return SumEA/PairCount;
+	}
+
+void CalcEADistMx(FILE *f, MultiSequence *sequences,
+  vector<vector<float> > &DistMx, vector<MySparseMx *> *SparsePostVec)
+	{
+	DistMx.clear();
+	const uint SeqCount = sequences->GetSeqCount();
+	DistMx.resize(SeqCount);
+	for (uint i = 0; i < SeqCount; ++i)
+		{
+		DistMx[i].resize(SeqCount, 0);
+		DistMx[i][i] = 1;
+		}
+	if (SparsePostVec != 0)
+		asserta(SIZE(*SparsePostVec) == 0);
+	if (SeqCount < 2)
+		return;
+	std::lock_guard<std::mutex> Guard(g_PairMutex);
+	EnsurePairCtx();
+	vector<uint> I1, I2;
+	vector<string> Labels1, Labels2;
+	for (uint i = 0; i < SeqCount; ++i)                 // GetAllPairs order: i<j row-major (getpairs.cpp)
+		for (uint j = i + 1; j < SeqCount; ++j)
+			{
+			I1.push_back(i);
+			I2.push_back(j);
+			Labels1.push_back(sequences->GetSequence(i)->m_Label);
+			Labels2.push_back(sequences->GetSequence(j)->m_Label);
+			}
+	const uint PairCount = SIZE(I1);
+	ProgressStep(0, 2, "%u consensus seqs (B200)", SeqCount);
+	vector<float> EAs;
+	RunPairList(Labels1, Labels2, EAs);
+	if (SparsePostVec != 0)
+		{
+		for (uint k = 0; k < PairCount; ++k)
+			{
+			MySparseMx *S = new MySparseMx;
+			S->m_LX = GetSeqLengthByGlobalLabel(Labels1[k]);
+			S->m_LY = GetSeqLengthByGlobalLabel(Labels2[k]);
+			SparsePostVec->push_back(S);
+			}
+		ExportSparse(Labels1, *SparsePostVec);
+		}
+	for (uint k = 0; k < PairCount; ++k)
+		{
+		DistMx[I1[k]][I2[k]] = EAs[k];
+		DistMx[I2[k]][I1[k]] = EAs[k];
+		if (f != 0)
+			fprintf(f, "%s\t%s\t%.4g\n", Labels1[k].c_str(), Labels2[k].c_str(), EAs[k]);
+		}
+	ProgressStep(1, 2, "%u consensus seqs (B200)", SeqCount);
+	}
+
+float AlignPairFlat_SparsePost(const string &Label1, const string &Label2,
+  string &Path, MySparseMx *SparsePost)
+	{
+	std::lock_guard<std::mutex> Guard(g_PairMutex);
+	EnsurePairCtx();
+	vector<string> L1(1, Label1), L2(1, Label2);
+	vector<float> EAs;
+	RunPairList(L1, L2, EAs);
+	const uint LX = GetSeqLengthByGlobalLabel(Label1);
+	const uint LY = GetSeqLengthByGlobalLabel(Label2);
+	// the decoding path: max-sum DP + traceback on the stored sparse posterior
+	uint StorePair = 0;
+	uint64_t PathOff[2] = { 0, uint64_t(LX) + LY + 1 };
+	vector<char> PathBuf(LX + LY + 2);
+	float Score = 0;
+	CheckP(mb200_align_pairs(g_PairCtx, 1, &StorePair, PathBuf.data(), PathOff, &Score), "mb200_align_pairs");
+	Path = string(PathBuf.data());
+	if (SparsePost != 0)
+		{
+		SparsePost->m_LX = LX;
+		SparsePost->m_LY = LY;
+		vector<MySparseMx *> One(1, SparsePost);
+		ExportSparse(L1, One);
+		}
+	return EAs[0];
+	}
+
+float AlignPairFlat(const string &Label1, const string &Label2, string &Path)
+	{
+	return AlignPairFlat_SparsePost(Label1, Label2, Path, 0);
+	}

@@ -35,5 +35,15 @@ def main():
 		print(name, "->", out)
 
 
+def super5():
+	seqs = synth.make_family(150, 90, 15, seed=104, n_sub=12)
+	fa = os.path.join(OUT, "super5_150.fa")
+	with open(fa, "w") as f:
+		for i, s in enumerate(seqs):
+			f.write(">s%d\n%s\n" % (i, s))
+	subprocess.run([CLI, "-super5", fa, "-output", os.path.join(OUT, "super5_150.ref.afa"), "-quiet"], check=True)
+
+
 if __name__ == "__main__":
+	super5()
 	main()

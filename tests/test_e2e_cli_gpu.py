@@ -61,3 +61,25 @@ def test_align_cli_matches_reference_msa(name, tmp_path):
 	a, b = pair_set(got), pair_set(want)
 	q = len(a & b)/max(1, len(b))
 	assert q >= 0.98, "MSA differs from the reference: shared aligned pairs %.4f" % q
+
+
+def test_super5_cli_matches_reference_msa(tmp_path):
+	"""`-super5` (UClust/EACluster -> AlignPairFlat, per-cluster MPCFlat, CalcEADistMx, PProg joins with
+	GetPostPairsAlignedFlat) with every CalcPost caller bound to the GPU engine
+	(integration/pairlist_b200_shim.cpp + mpcflat_b200_shim.cpp)."""
+	if not os.path.exists(CLI):
+		pytest.skip("integration/_build/muscle_b200 not built (needs /root/reference at build time)")
+	name = "super5_150"
+	out = tmp_path / (name + ".afa")
+	r = subprocess.run([CLI, "-super5", os.path.join(E2E, name + ".fa"), "-output", str(out), "-quiet"],
+	  capture_output=True, text=True, timeout=900)
+	assert r.returncode == 0, r.stderr[-2000:]
+	got, want = read_afa(out), read_afa(os.path.join(E2E, name + ".ref.afa"))
+	assert sorted(got) == sorted(want)
+	for n in want:
+		assert got[n].replace("-", "") == want[n].replace("-", "")
+	if got == want:
+		return
+	a, b = pair_set(got), pair_set(want)
+	q = len(a & b)/max(1, len(b))
+	assert q >= 0.98, "super5 MSA differs from the reference: shared aligned pairs %.4f" % q
