@@ -15,6 +15,12 @@
 #include <mutex>
 #include <unordered_map>
 
+// the reference's own (CPU) implementations, kept linked under C names by integration/Makefile
+extern "C" float REF_AlignPairFlat_SparsePost(const string &, const string &, string &, MySparseMx *);
+extern "C" void REF_CalcEADistMx(FILE *, MultiSequence *, vector<vector<float> > &, vector<MySparseMx *> *);
+extern "C" float REF_GetPostPairsAlignedFlat(PProg *, const string &, const MultiSequence &, const MultiSequence &,
+  const vector<uint> &, const vector<uint> &, vector<MySparseMx *> &);
+
 static mb200_ctx *g_PairCtx = 0;
 static std::mutex g_PairMutex;
 
@@ -114,6 +120,8 @@ float PProg::GetPostPairsAlignedFlat(const string &aProgressStr,
   const vector<uint> &SeqIndexes1, const vector<uint> &SeqIndexes2,
   vector<MySparseMx *> &SparsePosts)
 	{
+	if (getenv("MB200_CPU_PPROG") != 0)
+		return REF_GetPostPairsAlignedFlat(this, aProgressStr, MSA1, MSA2, SeqIndexes1, SeqIndexes2, SparsePosts);
 	const uint PairCount = SIZE(SeqIndexes1);
 	asserta(SIZE(SeqIndexes2) == PairCount);
 	asserta(SparsePosts.empty());
@@ -148,6 +156,11 @@ float PProg::GetPostPairsAlignedFlat(const string &aProgressStr,
 void CalcEADistMx(FILE *f, MultiSequence *sequences,
   vector<vector<float> > &DistMx, vector<MySparseMx *> *SparsePostVec)
 	{
+	if (getenv("MB200_CPU_EADIST") != 0)
+		{
+		REF_CalcEADistMx(f, sequences, DistMx, SparsePostVec);
+		return;
+		}
 	DistMx.clear();
 	const uint SeqCount = sequences->GetSeqCount();
 	DistMx.resize(SeqCount);
@@ -200,6 +213,8 @@ void CalcEADistMx(FILE *f, MultiSequence *sequences,
 float AlignPairFlat_SparsePost(const string &Label1, const string &Label2,
   string &Path, MySparseMx *SparsePost)
 	{
+	if (getenv("MB200_CPU_ALIGNPAIR") != 0)
+		return REF_AlignPairFlat_SparsePost(Label1, Label2, Path, SparsePost);
 	std::lock_guard<std::mutex> Guard(g_PairMutex);
 	EnsurePairCtx();
 	vector<string> L1(1, Label1), L2(1, Label2);

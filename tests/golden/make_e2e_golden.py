@@ -41,7 +41,10 @@ def super5():
 	with open(fa, "w") as f:
 		for i, s in enumerate(seqs):
 			f.write(">s%d\n%s\n" % (i, s))
-	subprocess.run([CLI, "-super5", fa, "-output", os.path.join(OUT, "super5_150.ref.afa"), "-quiet"], check=True)
+	# -threads 1: the reference's own -super5 is NOT reproducible with several threads (two runs of the
+	# unmodified binary share only ~60 % of their aligned residue pairs: OpenMP-order dependent
+	# decisions in EACluster/CalcEADistMx); single-threaded it is deterministic.
+	subprocess.run([CLI, "-super5", fa, "-output", os.path.join(OUT, "super5_150.ref.afa"), "-quiet", "-threads", "1"], check=True)
 
 
 if __name__ == "__main__":
