@@ -124,3 +124,17 @@ def test_errors(engine):
 	engine.set_seqs(["ACD", "EFG"])
 	with pytest.raises(MB200Error):
 		engine.posteriors([0], [5])
+
+
+def test_config4_scale_long_pair(engine, oracle):
+	"""BASELINE config 4 scale: one 1900 x 2600 pair (6 strips of 512 columns, 4.9e6 cells).
+	Forward/Backward/total bit-exact, posterior within tolerance, EA and sparse store consistent."""
+	s = synth.make_family(2, 2250, 350, seed=44)
+	X, Y = s[0][:1900], (s[1] + s[1])[:2600]
+	post, p = _dense_check(engine, oracle, X, Y)
+	engine.set_seqs([X, Y])
+	ea = engine.posteriors([0], [1])
+	off, ent = engine.export_pair(0)
+	off_o, ent_o = oracle.sparse(p)
+	_sparse_equal(off, ent, off_o, ent_o, "long pair")
+	assert abs(ea[0] - oracle.alnscore(p)/min(len(X), len(Y))) <= 1e-6
