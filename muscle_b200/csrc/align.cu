@@ -214,6 +214,100 @@ k_buildpost(const BuildPostParams P)
 		}
 	}
 
+// ---------------------------------------------------------------------------------------------
+// k_buildpost_warp: one WARP per row of Post with the row accumulator in shared memory.  The (s,t)
+// order of the reference is kept (s-major, t-minor, one term per (s,t) and cell), but the gather of
+// the sparse rows -- the latency-bound part of k_buildpost -- is done for 32 consecutive t at once:
+// lane l fetches row `pos` of S[s -> t0+l] (<= BP_W entries, already mapped to columns of B) into a
+// staging slot, then the warp applies the 32 staged rows strictly in t order, the entries of one
+// row in parallel (their target cells are distinct).  Rows longer than BP_W are applied by the
+// owning lane alone, still in order.
+#define BP_WARPS 4
+#define BP_W 8
+
+__global__ void __launch_bounds__(32*BP_WARPS)
+k_buildpost_warp(const BuildPostParams P)
+	{
+	extern __shared__ __align__(16) unsigned char bp_smem[];
+	const uint32_t wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const uint32_t row = blockIdx.x*BP_WARPS + wib;
+	float *acc = reinterpret_cast<float *>(bp_smem) + (size_t) wib*P.cols_b;
+	uint2 *stage = reinterpret_cast<uint2 *>(reinterpret_cast<float *>(bp_smem) + (size_t) BP_WARPS*P.cols_b)
+	  + (size_t) wib*32*BP_W;
+	if (row >= P.cols_a)
+		return;
+	for (uint32_t c = lane; c < P.cols_b; c += 32)
+		acc[c] = 0.0f;
+	__syncwarp();
+	for (uint32_t s = 0; s < P.na; ++s)
+		{
+		const int32_t pos = P.col2pos_a[(size_t) s*P.cols_a + row];
+		if (pos < 0)
+			continue;
+		const uint32_t a = P.ids_a[s];
+		for (uint32_t t0 = 0; t0 < P.nb; t0 += 32)
+			{
+			const uint32_t t = t0 + lane;
+			uint32_t n = 0, e0 = 0;
+			const mb200_entry *en = nullptr;
+			const uint32_t *p2c = nullptr;
+			if (t < P.nb)
+				{
+				const uint32_t b = P.ids_b[t];
+				const uint32_t *ro;
+				if (a < b)
+					{
+					const uint32_t q = (uint32_t)((uint64_t) a*P.n - (uint64_t) a*(a + 1)/2 + (b - a - 1));
+					ro = P.rowoff + P.rowbase[q]; en = P.entries + P.entbase[q];
+					}
+				else
+					{
+					const uint32_t q = (uint32_t)((uint64_t) b*P.n - (uint64_t) b*(b + 1)/2 + (a - b - 1));
+					ro = P.troff + P.trbase[q]; en = P.trentries + P.entbase[q];
+					}
+				e0 = ro[pos];
+				n = ro[pos + 1] - e0;
+				p2c = P.p2c_b + P.p2c_b_off[t];
+				const uint32_t m = min(n, (uint32_t) BP_W);
+				for (uint32_t k = 0; k < m; ++k)
+					{
+					const mb200_entry v = en[e0 + k];
+					stage[lane*BP_W + k] = make_uint2(p2c[v.col], __float_as_uint(v.p));
+					}
+				}
+			__syncwarp();
+			const uint32_t chunk = min(32u, P.nb - t0);
+			for (uint32_t l = 0; l < chunk; ++l)
+				{
+				const uint32_t nl = __shfl_sync(MB_FULL, n, l);
+				if (nl == 0)
+					continue;
+				if (nl <= BP_W)
+					{
+					if (lane < nl)
+						{
+						const uint2 v = stage[l*BP_W + lane];
+						acc[v.x] = __fadd_rn(acc[v.x], __uint_as_float(v.y));     // += w1*w2*P, unit weights
+						}
+					}
+				else if (lane == l)
+					{
+					for (uint32_t k = 0; k < n; ++k)
+						{
+						const mb200_entry v = en[e0 + k];
+						const uint32_t c2 = p2c[v.col];
+						acc[c2] = __fadd_rn(acc[c2], v.p);
+						}
+					}
+				__syncwarp();
+				}
+			}
+		}
+	float *prow = P.post + (size_t) row*P.cols_b;
+	for (uint32_t c = lane; c < P.cols_b; c += 32)
+		prow[c] = acc[c];
+	}
+
 extern "C" {
 
 int mb200_align_pairs(mb200_ctx *ctx, uint32_t n, const uint32_t *store_pairs, char *paths_out,
@@ -354,8 +448,18 @@ int mb200_align_groups(mb200_ctx *ctx, uint32_t na, const uint32_t *ids_a, const
 	P.trentries = (const mb200_entry *) ctx->d_tr_entries.p;
 	P.entbase = (const uint64_t *) ctx->d_entbase.p;
 	P.post = d_post;
-	const uint32_t groups_per_block = 128/8;
-	k_buildpost<<<(cols_a + groups_per_block - 1)/groups_per_block, 128, 0, st>>>(P);
+	const size_t bp_smem = (size_t) BP_WARPS*cols_b*sizeof(float) + (size_t) BP_WARPS*32*BP_W*sizeof(uint2);
+	if (bp_smem <= 160*1024)
+		{
+		CU(cudaFuncSetAttribute(k_buildpost_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bp_smem));
+		k_buildpost_warp<<<(cols_a + BP_WARPS - 1)/BP_WARPS, 32*BP_WARPS, bp_smem, st>>>(P);
+		}
+	else
+		{
+		// very wide alignments: row accumulators stay in global memory
+		const uint32_t groups_per_block = 128/8;
+		k_buildpost<<<(cols_a + groups_per_block - 1)/groups_per_block, 128, 0, st>>>(P);
+		}
 	CU(cudaGetLastError());
 	AlnProblem pr;
 	pr.LX = cols_a; pr.LY = cols_b; pr.dense = d_post; pr.rowoff = nullptr; pr.entries = nullptr;
