@@ -70,3 +70,20 @@ def test_family_decode(oracle):
 	z, seqs = _family()
 	sc, path = oracle.calcaln(z["post01"])
 	assert np.float32(sc) == z["score01"] and path.encode() == z["path01"].tobytes()
+
+
+def test_nucleotide_tables_and_kat():
+	"""nucleotide alphabet (4x4 table, U==T, wildcard for N/R/Y): oracle vs compiled-reference goldens"""
+	from oracle.pyoracle import Oracle
+	z = np.load(os.path.join(GOLDEN, "hmm_nucleo.npz"))
+	t = {k: z[k] for k in ("start", "trans", "ins", "match", "min_sparse_score")}
+	assert t["match"].reshape(256, 256)[ord("U"), ord("A")] == t["match"].reshape(256, 256)[ord("T"), ord("A")]
+	O = Oracle(t)
+	k = np.load(os.path.join(GOLDEN, "kat_nucleo.npz"))
+	for i in range(int(k["n"])):
+		X, Y = k["x%d" % i].tobytes(), k["y%d" % i].tobytes()
+		f, b = O.fwd(X, Y), O.bwd(X, Y)
+		assert np.ascontiguousarray(f[1:, 1:, 0]).tobytes() == k["fwdm%d" % i].tobytes()
+		assert np.ascontiguousarray(b[1:, 1:, 0]).tobytes() == k["bwdm%d" % i].tobytes()
+		assert np.float32(O.total(f, b)) == k["total%d" % i]
+		assert O.post(X, Y).tobytes() == k["post%d" % i].tobytes()

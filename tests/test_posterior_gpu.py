@@ -138,3 +138,41 @@ def test_config4_scale_long_pair(engine, oracle):
 	off_o, ent_o = oracle.sparse(p)
 	_sparse_equal(off, ent, off_o, ent_o, "long pair")
 	assert abs(ea[0] - oracle.alnscore(p)/min(len(X), len(Y))) <= 1e-6
+
+
+def test_nucleotide_alphabet(tables):
+	"""a second set of HMM tables (nucleotides, 6 residue classes instead of 21) through the same kernels"""
+	from muscle_b200.engine import Engine
+	z = np.load(os.path.join(GOLDEN, "hmm_nucleo.npz"))
+	t = {k: z[k] for k in ("start", "trans", "ins", "match", "min_sparse_score")}
+	k = np.load(os.path.join(GOLDEN, "kat_nucleo.npz"))
+	e = Engine(0)
+	e.set_hmm(t)
+	for i in range(int(k["n"])):
+		X, Y = k["x%d" % i].tobytes(), k["y%d" % i].tobytes()
+		e.set_seqs([X, Y])
+		post, fwd, bwd, tot = e.calc_post_dense(0, 1)
+		assert fwd.tobytes() == k["fwdm%d" % i].tobytes() and bwd.tobytes() == k["bwdm%d" % i].tobytes()
+		assert np.float32(tot) == k["total%d" % i]
+		assert np.abs(post - k["post%d" % i]).max() <= POST_TOL
+		ea = e.posteriors([0], [1])
+		assert abs(ea[0] - float(k["alnscore%d" % i])/min(len(X), len(Y))) <= 1e-6
+	# tables can be swapped on a live context (the reference rewrites them between replicates)
+	e.set_hmm(tables)
+	e.close()
+
+
+def test_guards_and_bad_input(engine):
+	"""reference guard LX*LY*5+100 > INT_MAX (fwdflat3.cpp:17) and argument checking: errors, no compute"""
+	from muscle_b200.engine import MB200Error
+	long_a, long_b = "A"*21000, "C"*21000
+	engine.set_seqs([long_a, long_b, "ACD"])
+	with pytest.raises(MB200Error) as ei:
+		engine.posteriors([0], [1])
+	assert ei.value.code == -5 and "HMM overflow" in str(ei.value)
+	engine.posteriors([0], [2])                           # 21000 x 3 is fine
+	with pytest.raises(MB200Error):
+		engine.set_seqs(["ACD", ""])                       # empty sequence: the reference would read X[0]
+	engine.set_seqs(["ACD", "EFG"])
+	with pytest.raises(MB200Error):
+		engine.consistency_iter()                          # store is not an all-pairs store yet
