@@ -270,12 +270,18 @@ def main():
 		# dominant kernel k_posterior<C> (one launch per column-width bin): live CUDA-event time of the
 		# launches of this rank, algorithmic bytes = 12 B/cell x cells of this rank
 		achieved = ALGO_BYTES_PER_CELL*my_cells*steps/(kern_ms*1e-3)/1e9
+		# DRAM traffic and instruction count per cell come from the committed ncu capture of this kernel
+		# (profiles/traffic_bytes_per_cell.json); both are per step here (one step = the launches of all
+		# size classes), like `achieved`
 		traffic = None
+		winst_per_cell = None
 		tp = os.path.join(ROOT, "profiles", "traffic_bytes_per_cell.json")
 		if os.path.exists(tp):
 			try:
 				with open(tp) as f:
-					traffic = json.load(f).get("dram_bytes_per_cell", None)
+					prof = json.load(f)
+				traffic = prof.get("dram_bytes_per_cell", None)
+				winst_per_cell = prof.get("warp_inst_per_cell", None)
 				if traffic is not None:
 					traffic = traffic*my_cells
 			except Exception:
@@ -292,7 +298,13 @@ def main():
 		    "algorithmic_bytes_per_cell": ALGO_BYTES_PER_CELL,
 		    "kernel_ms_per_step": kern_ms/steps,
 		    "note": "kernel is fp32-issue bound, not HBM bound (SURVEY.md 8d): see issue_gflops",
-		    "issue_gflops": ISSUE_FLOP_PER_CELL*my_cells*steps/(kern_ms*1e-3)/1e9},
+		    "issue_gflops": ISSUE_FLOP_PER_CELL*my_cells*steps/(kern_ms*1e-3)/1e9,
+		    "issue": None if not (winst_per_cell and clocks and clocks.get("sm_mhz")) else {
+		      "what": "warp-instructions issued per second vs 148 SMs x 4 schedulers x SM clock (1 issue/clk each)",
+		      "warp_inst_per_cell": winst_per_cell,
+		      "achieved_ginst": winst_per_cell*my_cells*steps/(kern_ms*1e-3)/1e9,
+		      "peak_ginst": 148*4*clocks["sm_mhz"]*1e6/1e9,
+		      "frac": winst_per_cell*my_cells*steps/(kern_ms*1e-3)/(148*4*clocks["sm_mhz"]*1e6)}},
 		  "device_ms_per_step": dev_ms_max/steps}
 		if not args.no_cpu_baseline and world == 1:
 			out["cpu_baseline"] = cpu_reference_run(seqs, 0, seconds=args.cpu_seconds)
