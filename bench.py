@@ -263,8 +263,10 @@ def main():
 
 	if rank == 0:
 		steps = args.steps
-		# value: whole-job cells over the max-over-ranks time of the timed region (barrier to barrier)
-		value = total_cells*steps/wall_max
+		# value: whole-job cells over the max-over-ranks DEVICE time of the K timed steps (CUDA events on
+		# the library's launching stream, first launch to last completion of every step); the
+		# barrier-to-barrier wall clock of the same region is reported beside it
+		value = total_cells*steps/(dev_ms_max*1e-3)
 		e2e_value = total_cells*steps/wall_e2e_max
 		peak, peak_src = load_peaks()
 		# dominant kernel k_posterior<C> (one launch per column-width bin): live CUDA-event time of the
@@ -287,7 +289,8 @@ def main():
 			except Exception:
 				traffic = None
 		out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": max(3, args.warmup),
-		  "ms_per_step": 1e3*wall_max/steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+		  "ms_per_step": dev_ms_max/steps, "wall_ms_per_step": 1e3*wall_max/steps, "higher_is_better": True,
+		  "scaling": "strong", "vs_baseline": None,
 		  "dtype": "f32", "data": "synthetic", "config": config,
 		  "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
 		    "what": "mb200_set_seqs(host bytes) + mb200_posteriors_allpairs -> EA on host; sparse store stays in HBM for the next stage"},
