@@ -14,7 +14,21 @@
 #include "pairhmm.h"
 #include "../include/muscle_b200.h"
 
+#include <chrono>
 static mb200_ctx *g_Ctx = 0;
+
+// MB200_TRACE=1: wall-time split of the replaced members, printed at exit
+static double g_TPrep = 0, g_TLib = 0, g_TGaps = 0, g_TPost = 0, g_TCons = 0;
+static uint g_NAlign = 0;
+static double Now()
+	{
+	return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+	}
+static void TraceReport()
+	{
+	fprintf(stderr, "\n[mb200 trace] CalcPosteriors %.2f s, ConsIter %.2f s, AlignAlns x%u: prepare %.2f s, "
+	  "mb200_align_groups %.2f s, AddGapsPath %.2f s\n", g_TPost, g_TCons, g_NAlign, g_TPrep, g_TLib, g_TGaps);
+	}
 
 static void Check(int rc, const char *What)
 	{
@@ -33,10 +47,13 @@ static void EnsureCtx()
 	int rc = mb200_create(Device, &g_Ctx);
 	if (rc != MB200_OK)
 		Die("libmuscle_b200 mb200_create failed (%d): %s", rc, mb200_last_error(0));
+	if (getenv("MB200_TRACE") != 0)
+		atexit(TraceReport);
 	}
 
 void MPCFlat::CalcPosteriors()
 	{
+	const double T0 = Now();
 	EnsureCtx();
 	const uint SeqCount = GetSeqCount();
 	const uint PairCount = SIZE(m_Pairs);
@@ -70,6 +87,7 @@ void MPCFlat::CalcPosteriors()
 		m_DistMx[Pair.second][Pair.first] = EA;
 		}
 	ProgressStep(1, 2, "Calc posteriors (B200)");
+	g_TPost += Now() - T0;
 	// The sparse posteriors stay resident in HBM for ConsIter / AlignAlns (the store replaces
 	// m_SparsePosts1/2).  Set MB200_EXPORT_SPARSE=1 to also fill the host MySparseMx objects, e.g.
 	// for commands that read GetSparsePost() directly (-profalign).
@@ -100,7 +118,9 @@ void MPCFlat::ConsIter(uint Iter)
 	const uint PairCount = SIZE(m_Pairs);
 	asserta(PairCount > 0);
 	ProgressStep(0, 2, "Consistency (%u/%u) (B200)", Iter + 1, m_ConsistencyIterCount);
+	const double T0 = Now();
 	Check(mb200_consistency_iter(g_Ctx, 0, PairCount), "mb200_consistency_iter");
+	g_TCons += Now() - T0;
 	ProgressStep(1, 2, "Consistency (%u/%u) (B200)", Iter + 1, m_ConsistencyIterCount);
 	// the Jacobi buffer swap (consflat.cpp:22) happens inside the library
 	}
@@ -108,6 +128,8 @@ void MPCFlat::ConsIter(uint Iter)
 MultiSequence *MPCFlat::AlignAlns(const MultiSequence &MSA1, const MultiSequence &MSA2, float *ptrScore)
 	{
 	EnsureCtx();
+	const double T0 = Now();
+	++g_NAlign;
 	const uint SeqCount1 = MSA1.GetSeqCount();
 	const uint SeqCount2 = MSA2.GetSeqCount();
 	const uint ColCount1 = MSA1.GetColCount();
@@ -131,8 +153,12 @@ MultiSequence *MPCFlat::AlignAlns(const MultiSequence &MSA1, const MultiSequence
 
 	vector<char> PathBuf(ColCount1 + ColCount2 + 1);
 	float Score = 0;
+	const double T1 = Now();
+	g_TPrep += T1 - T0;
 	Check(mb200_align_groups(g_Ctx, SeqCount1, Ids1.data(), P2C1.data(), ColCount1,
 	  SeqCount2, Ids2.data(), P2C2.data(), ColCount2, PathBuf.data(), &Score, 0), "mb200_align_groups");
+	const double T2 = Now();
+	g_TLib += T2 - T1;
 	if (ptrScore != 0)
 		*ptrScore = Score;
 	const string Path(PathBuf.data());
@@ -151,5 +177,6 @@ MultiSequence *MPCFlat::AlignAlns(const MultiSequence &MSA1, const MultiSequence
 		Sequence *AlignedRow = InputRow->AddGapsPath(Path, 'Y');
 		result->AddSequence(AlignedRow, true);
 		}
+	g_TGaps += Now() - T2;
 	return result;
 	}
