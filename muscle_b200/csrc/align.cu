@@ -214,96 +214,139 @@ k_buildpost(const BuildPostParams P)
 		}
 	}
 
-// ---------------------------------------------------------------------------------------------
-// k_buildpost_warp: one WARP per row of Post with the row accumulator in shared memory.  The (s,t)
-// order of the reference is kept (s-major, t-minor, one term per (s,t) and cell), but the gather of
-// the sparse rows -- the latency-bound part of k_buildpost -- is done for 32 consecutive t at once:
-// lane l fetches row `pos` of S[s -> t0+l] (<= BP_W entries, already mapped to columns of B) into a
-// staging slot, then the warp applies the 32 staged rows strictly in t order, the entries of one
-// row in parallel (their target cells are distinct).  Rows longer than BP_W are applied by the
-// owning lane alone, still in order.
 #define BP_WARPS 4
 #define BP_W 8
 
+// ---------------------------------------------------------------------------------------------
+// Two-phase BuildPost (default).  The direct formulation (k_buildpost: one lane group per row walking all (s,t)) is
+// latency bound: every (s,t) step chains 4-5 dependent random loads into the 10 GB store and only
+// cols_a groups exist (C3 trace: 44 ms per AlignAlns call, 49 s of a 110 s `muscle -align`).  Here the random gathers are done by a
+// massively parallel pre-pass -- one THREAD per (row, s, t) copies the <= BP_W entries of the needed
+// sparse row, already mapped to columns of B, into a dense staging slot -- and the order-sensitive
+// accumulation then streams the staging area with coalesced loads.  The fp32 sum order of the
+// reference (s-major, t-minor) is unchanged, so the result stays bit-identical.
+struct BpStage
+	{
+	uint2   *slots;      // [row][s_local][t][BP_W]  (column of B, bits of P)
+	uint8_t *cnt;        // [row][s_local][t]; 255 = row longer than BP_W (applied by direct gather)
+	uint32_t s_lo, s_n;  // batch of sequences of A
+	};
+
+__global__ void __launch_bounds__(256)
+k_bp_gather(const BuildPostParams P, const BpStage G)
+	{
+	const uint64_t total = (uint64_t) P.cols_a*G.s_n*P.nb;
+	for (uint64_t idx = blockIdx.x*(uint64_t) blockDim.x + threadIdx.x; idx < total; idx += (uint64_t) gridDim.x*blockDim.x)
+		{
+		const uint32_t t = (uint32_t)(idx % P.nb);
+		const uint64_t rs = idx/P.nb;
+		const uint32_t sl = (uint32_t)(rs % G.s_n);
+		const uint32_t row = (uint32_t)(rs/G.s_n);
+		const uint32_t s = G.s_lo + sl;
+		const int32_t pos = P.col2pos_a[(size_t) s*P.cols_a + row];
+		uint32_t n = 0;
+		if (pos >= 0)
+			{
+			const uint32_t a = P.ids_a[s], b = P.ids_b[t];
+			const uint32_t *ro;
+			const mb200_entry *en;
+			if (a < b)
+				{
+				const uint32_t q = (uint32_t)((uint64_t) a*P.n - (uint64_t) a*(a + 1)/2 + (b - a - 1));
+				ro = P.rowoff + P.rowbase[q]; en = P.entries + P.entbase[q];
+				}
+			else
+				{
+				const uint32_t q = (uint32_t)((uint64_t) b*P.n - (uint64_t) b*(b + 1)/2 + (a - b - 1));
+				ro = P.troff + P.trbase[q]; en = P.trentries + P.entbase[q];
+				}
+			const uint32_t e0 = ro[pos];
+			n = ro[pos + 1] - e0;
+			if (n <= BP_W)
+				{
+				const uint32_t *p2c = P.p2c_b + P.p2c_b_off[t];
+				uint2 *dst = G.slots + idx*BP_W;
+				for (uint32_t k = 0; k < n; ++k)
+					{
+					const mb200_entry v = en[e0 + k];
+					dst[k] = make_uint2(p2c[v.col], __float_as_uint(v.p));
+					}
+				}
+			else
+				n = 255;
+			}
+		G.cnt[idx] = (uint8_t) n;
+		}
+	}
+
 __global__ void __launch_bounds__(32*BP_WARPS)
-k_buildpost_warp(const BuildPostParams P)
+k_bp_apply(const BuildPostParams P, const BpStage G)
 	{
 	extern __shared__ __align__(16) unsigned char bp_smem[];
 	const uint32_t wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	const uint32_t row = blockIdx.x*BP_WARPS + wib;
 	float *acc = reinterpret_cast<float *>(bp_smem) + (size_t) wib*P.cols_b;
-	uint2 *stage = reinterpret_cast<uint2 *>(reinterpret_cast<float *>(bp_smem) + (size_t) BP_WARPS*P.cols_b)
-	  + (size_t) wib*32*BP_W;
 	if (row >= P.cols_a)
 		return;
+	float *prow = P.post + (size_t) row*P.cols_b;
 	for (uint32_t c = lane; c < P.cols_b; c += 32)
-		acc[c] = 0.0f;
+		acc[c] = prow[c];
 	__syncwarp();
-	for (uint32_t s = 0; s < P.na; ++s)
+	for (uint32_t sl = 0; sl < G.s_n; ++sl)
 		{
+		const uint32_t s = G.s_lo + sl;
 		const int32_t pos = P.col2pos_a[(size_t) s*P.cols_a + row];
 		if (pos < 0)
 			continue;
-		const uint32_t a = P.ids_a[s];
+		const uint64_t base = ((uint64_t) row*G.s_n + sl)*P.nb;
 		for (uint32_t t0 = 0; t0 < P.nb; t0 += 32)
 			{
 			const uint32_t t = t0 + lane;
-			uint32_t n = 0, e0 = 0;
-			const mb200_entry *en = nullptr;
-			const uint32_t *p2c = nullptr;
-			if (t < P.nb)
-				{
-				const uint32_t b = P.ids_b[t];
-				const uint32_t *ro;
-				if (a < b)
-					{
-					const uint32_t q = (uint32_t)((uint64_t) a*P.n - (uint64_t) a*(a + 1)/2 + (b - a - 1));
-					ro = P.rowoff + P.rowbase[q]; en = P.entries + P.entbase[q];
-					}
-				else
-					{
-					const uint32_t q = (uint32_t)((uint64_t) b*P.n - (uint64_t) b*(b + 1)/2 + (a - b - 1));
-					ro = P.troff + P.trbase[q]; en = P.trentries + P.entbase[q];
-					}
-				e0 = ro[pos];
-				n = ro[pos + 1] - e0;
-				p2c = P.p2c_b + P.p2c_b_off[t];
-				const uint32_t m = min(n, (uint32_t) BP_W);
-				for (uint32_t k = 0; k < m; ++k)
-					{
-					const mb200_entry v = en[e0 + k];
-					stage[lane*BP_W + k] = make_uint2(p2c[v.col], __float_as_uint(v.p));
-					}
-				}
-			__syncwarp();
+			const uint32_t n = t < P.nb ? (uint32_t) G.cnt[base + t] : 0u;
+			const uint32_t any = __ballot_sync(MB_FULL, n != 0);
+			if (any == 0)
+				continue;
 			const uint32_t chunk = min(32u, P.nb - t0);
 			for (uint32_t l = 0; l < chunk; ++l)
 				{
-				const uint32_t nl = __shfl_sync(MB_FULL, n, l);
-				if (nl == 0)
+				if (!((any >> l) & 1u))
 					continue;
-				if (nl <= BP_W)
+				const uint32_t nl = __shfl_sync(MB_FULL, n, l);
+				if (nl != 255)
 					{
 					if (lane < nl)
 						{
-						const uint2 v = stage[l*BP_W + lane];
+						const uint2 v = G.slots[(base + t0 + l)*BP_W + lane];
 						acc[v.x] = __fadd_rn(acc[v.x], __uint_as_float(v.y));     // += w1*w2*P, unit weights
 						}
 					}
-				else if (lane == l)
+				else if (lane == 0)
 					{
-					for (uint32_t k = 0; k < n; ++k)
+					// rare: more than BP_W entries in the sparse row -> gather directly, still in order
+					const uint32_t a = P.ids_a[s], b = P.ids_b[t0 + l];
+					const uint32_t *ro;
+					const mb200_entry *en;
+					if (a < b)
 						{
-						const mb200_entry v = en[e0 + k];
-						const uint32_t c2 = p2c[v.col];
-						acc[c2] = __fadd_rn(acc[c2], v.p);
+						const uint32_t q = (uint32_t)((uint64_t) a*P.n - (uint64_t) a*(a + 1)/2 + (b - a - 1));
+						ro = P.rowoff + P.rowbase[q]; en = P.entries + P.entbase[q];
+						}
+					else
+						{
+						const uint32_t q = (uint32_t)((uint64_t) b*P.n - (uint64_t) b*(b + 1)/2 + (a - b - 1));
+						ro = P.troff + P.trbase[q]; en = P.trentries + P.entbase[q];
+						}
+					const uint32_t *p2c = P.p2c_b + P.p2c_b_off[t0 + l];
+					for (uint32_t e = ro[pos]; e < ro[pos + 1]; ++e)
+						{
+						const uint32_t c2 = p2c[en[e].col];
+						acc[c2] = __fadd_rn(acc[c2], en[e].p);
 						}
 					}
 				__syncwarp();
 				}
 			}
 		}
-	float *prow = P.post + (size_t) row*P.cols_b;
 	for (uint32_t c = lane; c < P.cols_b; c += 32)
 		prow[c] = acc[c];
 	}
@@ -448,11 +491,27 @@ int mb200_align_groups(mb200_ctx *ctx, uint32_t na, const uint32_t *ids_a, const
 	P.trentries = (const mb200_entry *) ctx->d_tr_entries.p;
 	P.entbase = (const uint64_t *) ctx->d_entbase.p;
 	P.post = d_post;
-	const size_t bp_smem = (size_t) BP_WARPS*cols_b*sizeof(float) + (size_t) BP_WARPS*32*BP_W*sizeof(uint2);
-	if (bp_smem <= 160*1024)
+	const size_t acc_smem = (size_t) BP_WARPS*cols_b*sizeof(float);
+	if (acc_smem <= 160*1024)
 		{
-		CU(cudaFuncSetAttribute(k_buildpost_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bp_smem));
-		k_buildpost_warp<<<(cols_a + BP_WARPS - 1)/BP_WARPS, 32*BP_WARPS, bp_smem, st>>>(P);
+		// batches of sequences of A sized so that the staging area stays below ~512 MB
+		const uint64_t per_s = (uint64_t) cols_a*nb*(BP_W*sizeof(uint2) + 1);
+		uint32_t sb = (uint32_t) std::max<uint64_t>(1, std::min<uint64_t>(na, (512ull << 20)/std::max<uint64_t>(per_s, 1)));
+		ENSURE(ctx->d_tmp2, (uint64_t) cols_a*sb*nb*BP_W*sizeof(uint2) + (uint64_t) cols_a*sb*nb + 64);
+		BpStage G;
+		G.slots = (uint2 *) ctx->d_tmp2.p;
+		G.cnt = (uint8_t *)(G.slots + (uint64_t) cols_a*sb*nb*BP_W);
+		CU(cudaFuncSetAttribute(k_bp_apply, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) acc_smem));
+		for (uint32_t s_lo = 0; s_lo < na; s_lo += sb)
+			{
+			G.s_lo = s_lo;
+			G.s_n = std::min(sb, na - s_lo);
+			const uint64_t total = (uint64_t) cols_a*G.s_n*nb;
+			const uint32_t gblocks = (uint32_t) std::min<uint64_t>((total + 255)/256, (uint64_t) ctx->prop.multiProcessorCount*32);
+			k_bp_gather<<<gblocks, 256, 0, st>>>(P, G);
+			k_bp_apply<<<(cols_a + BP_WARPS - 1)/BP_WARPS, 32*BP_WARPS, acc_smem, st>>>(P, G);
+			ctx->stats.kernel_launches += 2;
+			}
 		}
 	else
 		{
