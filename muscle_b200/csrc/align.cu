@@ -286,6 +286,10 @@ k_bp_apply(const BuildPostParams P, const BpStage G)
 	const uint32_t wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	const uint32_t row = blockIdx.x*BP_WARPS + wib;
 	float *acc = reinterpret_cast<float *>(bp_smem) + (size_t) wib*P.cols_b;
+	// per-warp copy of the 32 staged rows of the current chunk (the ordered apply must not wait on
+	// one global load per (s,t))
+	uint2 *stage = reinterpret_cast<uint2 *>(bp_smem + (((size_t) BP_WARPS*P.cols_b*sizeof(float) + 15) & ~(size_t) 15))
+	  + (size_t) wib*32*BP_W;
 	if (row >= P.cols_a)
 		return;
 	float *prow = P.post + (size_t) row*P.cols_b;
@@ -306,17 +310,26 @@ k_bp_apply(const BuildPostParams P, const BpStage G)
 			const uint32_t any = __ballot_sync(MB_FULL, n != 0);
 			if (any == 0)
 				continue;
-			const uint32_t chunk = min(32u, P.nb - t0);
-			for (uint32_t l = 0; l < chunk; ++l)
+			if (n != 0 && n != 255)
 				{
-				if (!((any >> l) & 1u))
-					continue;
+				const uint4 *src = reinterpret_cast<const uint4 *>(G.slots + (base + t)*BP_W);
+				uint4 *dst = reinterpret_cast<uint4 *>(stage + lane*BP_W);
+#pragma unroll
+				for (int k = 0; k < (int)(BP_W*sizeof(uint2)/sizeof(uint4)); ++k)
+					dst[k] = src[k];
+				}
+			__syncwarp();
+			uint32_t rest = any;
+			while (rest)
+				{
+				const uint32_t l = __ffs(rest) - 1;
+				rest &= rest - 1;
 				const uint32_t nl = __shfl_sync(MB_FULL, n, l);
 				if (nl != 255)
 					{
 					if (lane < nl)
 						{
-						const uint2 v = G.slots[(base + t0 + l)*BP_W + lane];
+						const uint2 v = stage[l*BP_W + lane];
 						acc[v.x] = __fadd_rn(acc[v.x], __uint_as_float(v.y));     // += w1*w2*P, unit weights
 						}
 					}
@@ -491,7 +504,7 @@ int mb200_align_groups(mb200_ctx *ctx, uint32_t na, const uint32_t *ids_a, const
 	P.trentries = (const mb200_entry *) ctx->d_tr_entries.p;
 	P.entbase = (const uint64_t *) ctx->d_entbase.p;
 	P.post = d_post;
-	const size_t acc_smem = (size_t) BP_WARPS*cols_b*sizeof(float);
+	const size_t acc_smem = (((size_t) BP_WARPS*cols_b*sizeof(float) + 15) & ~(size_t) 15) + (size_t) BP_WARPS*32*BP_W*sizeof(uint2);
 	if (acc_smem <= 160*1024)
 		{
 		// batches of sequences of A sized so that the staging area stays below ~512 MB
