@@ -22,6 +22,24 @@
 
 #define ALN_THREADS 256
 
+// MB200_TRACE=1: wall-time split of mb200_align_groups, printed at process exit
+#include <chrono>
+#include <cstdlib>
+#include <cstdio>
+static bool g_trace = false;
+static double g_t[6] = { 0, 0, 0, 0, 0, 0 };
+static unsigned g_calls = 0;
+static double now_s()
+	{
+	return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+	}
+static void trace_report()
+	{
+	fprintf(stderr, "[mb200 trace] align_groups x%u: host prep %.2f s, upload+memset %.2f s, gather %.2f s, apply %.2f s, "
+	  "decode DP %.2f s, download %.2f s\n", g_calls, g_t[0], g_t[1], g_t[2], g_t[3], g_t[4], g_t[5]);
+	}
+#define TRACE_MARK(k) do { if (g_trace) { cudaStreamSynchronize(st); const double n_ = now_s(); g_t[k] += n_ - tmark; tmark = n_; } } while (0)
+
 struct AlnProblem
 	{
 	uint32_t LX, LY;
@@ -434,9 +452,19 @@ int mb200_align_groups(mb200_ctx *ctx, uint32_t na, const uint32_t *ids_a, const
 		return mb_fail(ctx, MB200_EINVAL, "mb200_align_groups: the store must hold all N(N-1)/2 pairs");
 	cudaSetDevice(ctx->device);
 	cudaStream_t st = ctx->stream;
+	static bool trace_init = false;
+	if (!trace_init)
+		{
+		trace_init = true;
+		g_trace = getenv("MB200_TRACE") != nullptr;
+		if (g_trace)
+			atexit(trace_report);
+		}
 	int rc = mb_store_build_transposed(ctx);
 	if (rc != MB200_OK)
 		return rc;
+	double tmark = now_s();
+	++g_calls;
 	if (ctx->tr_values_stale)
 		{
 		rc = mb_store_refresh_transposed(ctx);
@@ -488,6 +516,7 @@ int mb200_align_groups(mb200_ctx *ctx, uint32_t na, const uint32_t *ids_a, const
 	uint64_t *d_boff = (uint64_t *) base;            base += al16(nb*8);
 	uint32_t *d_ida = (uint32_t *) base;             base += al16(na*4);
 	uint32_t *d_idb = (uint32_t *) base;
+	TRACE_MARK(0);
 	CU(cudaMemsetAsync(d_post, 0, post_bytes, st));
 	CU(cudaMemcpyAsync(d_c2p, c2p.data(), c2p.size()*4, cudaMemcpyHostToDevice, st));
 	CU(cudaMemcpyAsync(d_p2cb, pos2col_b, btot*4, cudaMemcpyHostToDevice, st));
@@ -504,6 +533,7 @@ int mb200_align_groups(mb200_ctx *ctx, uint32_t na, const uint32_t *ids_a, const
 	P.trentries = (const mb200_entry *) ctx->d_tr_entries.p;
 	P.entbase = (const uint64_t *) ctx->d_entbase.p;
 	P.post = d_post;
+	TRACE_MARK(1);
 	const size_t acc_smem = (((size_t) BP_WARPS*cols_b*sizeof(float) + 15) & ~(size_t) 15) + (size_t) BP_WARPS*32*BP_W*sizeof(uint2);
 	if (acc_smem <= 160*1024)
 		{
@@ -522,7 +552,9 @@ int mb200_align_groups(mb200_ctx *ctx, uint32_t na, const uint32_t *ids_a, const
 			const uint64_t total = (uint64_t) cols_a*G.s_n*nb;
 			const uint32_t gblocks = (uint32_t) std::min<uint64_t>((total + 255)/256, (uint64_t) ctx->prop.multiProcessorCount*32);
 			k_bp_gather<<<gblocks, 256, 0, st>>>(P, G);
+			TRACE_MARK(2);
 			k_bp_apply<<<(cols_a + BP_WARPS - 1)/BP_WARPS, 32*BP_WARPS, acc_smem, st>>>(P, G);
+			TRACE_MARK(3);
 			ctx->stats.kernel_launches += 2;
 			}
 		}
@@ -544,12 +576,14 @@ int mb200_align_groups(mb200_ctx *ctx, uint32_t na, const uint32_t *ids_a, const
 	k_alnflat<<<1, ALN_THREADS, smem, st>>>(d_prob);
 	CU(cudaGetLastError());
 	ctx->stats.kernel_launches += 2;
+	TRACE_MARK(4);
 	CU(cudaMemcpyAsync(path_out, d_path, cols_a + cols_b + 1, cudaMemcpyDeviceToHost, st));
 	if (score_out)
 		CU(cudaMemcpyAsync(score_out, d_score, sizeof(float), cudaMemcpyDeviceToHost, st));
 	if (post_out)
 		CU(cudaMemcpyAsync(post_out, d_post, post_bytes, cudaMemcpyDeviceToHost, st));
 	CU(cudaStreamSynchronize(st));
+	TRACE_MARK(5);
 	ctx->stats.d2h_bytes += cols_a + cols_b + 1 + 4 + (post_out ? post_bytes : 0);
 	return MB200_OK;
 	}
