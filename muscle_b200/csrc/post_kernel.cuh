@@ -366,7 +366,7 @@ k_posterior(const PostParams P)
 						const float score = __fsub_rn(ADD(fmv[c], M[c]), total);
 						if (col < LY && score >= h.minScore)
 							{
-							const float p = score >= 0.0f ? 1.0f : expf(score);
+							const float p = score >= 0.0f ? 1.0f : mb_expf_glibc(score);
 							if (cnt < MB_CAP)
 								{
 								row[cnt].p = p;
@@ -391,7 +391,7 @@ k_posterior(const PostParams P)
 								P.dbg_bwd[(size_t)(i - 1)*LY + col] = M[c];
 								const float score = __fsub_rn(ADD(fmv[c], M[c]), total);
 								P.dbg_post[(size_t)(i - 1)*LY + col] =
-								  score < h.minScore ? 0.0f : (score >= 0.0f ? 1.0f : expf(score));
+								  score < h.minScore ? 0.0f : (score >= 0.0f ? 1.0f : mb_expf_glibc(score));
 								}
 							}
 						}

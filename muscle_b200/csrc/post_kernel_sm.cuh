@@ -311,7 +311,7 @@ MB_UNROLL(MB_SM_UNROLL)
 						const float score = __fsub_rn(ADD(fmv, m), total);
 						if (col < LY && score >= h.minScore)
 							{
-							const float p = score >= 0.0f ? 1.0f : expf(score);
+							const float p = score >= 0.0f ? 1.0f : mb_expf_glibc(score);
 							if (cnt < MB_CAP)
 								{
 								row[cnt].p = p;
@@ -326,7 +326,7 @@ MB_UNROLL(MB_SM_UNROLL)
 							{
 							P.dbg_bwd[(size_t)(i - 1)*LY + col] = m;
 							P.dbg_post[(size_t)(i - 1)*LY + col] =
-							  score < h.minScore ? 0.0f : (score >= 0.0f ? 1.0f : expf(score));
+							  score < h.minScore ? 0.0f : (score >= 0.0f ? 1.0f : mb_expf_glibc(score));
 							}
 						}
 					outM = mFirst; outIY = riy; outJY = rjy;

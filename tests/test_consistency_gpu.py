@@ -49,8 +49,7 @@ def test_consistency_bitexact_vs_oracle(engine, oracle, n, L, seed):
 
 
 def test_consistency_golden_family8(engine):
-	"""against the compiled reference's own output (tests/golden/family8.npz): same pattern,
-	values within 1e-6 (the inputs differ by the expf ulp)."""
+	"""against the compiled reference's own output (tests/golden/family8.npz): bit-exact"""
 	z = np.load(os.path.join(GOLDEN, "family8.npz"))
 	seqs = [z["seq%d" % i].tobytes() for i in range(int(z["n"]))]
 	engine.set_seqs(seqs)
@@ -59,9 +58,7 @@ def test_consistency_golden_family8(engine):
 		engine.consistency_iter()
 		offs, ents = engine.export_all()
 		for p in range(len(offs)):
-			g = z["ent%d_%d" % (it, p)]
-			if len(g) == len(ents[p]) and (g["col"] == ents[p]["col"]).all():
-				assert np.abs(g["p"] - ents[p]["p"]).max(initial=0) <= 1e-6
+			assert z["ent%d_%d" % (it, p)].tobytes() == ents[p].tobytes(), (it, p)
 
 
 def test_consistency_partial_range_and_values_exchange(engine, oracle):

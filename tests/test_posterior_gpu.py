@@ -1,10 +1,9 @@
 """GPU parity of the fused posterior kernel (through the C ABI) against the CPU oracle.
 
-Tolerances: Forward-M, Backward-M and the total log-probability are compared BIT-EXACT (every
-operation is an IEEE add/mul in the reference's order).  Posterior cells go through expf, where
-CUDA's expf and glibc's differ by <= 2 ulp, so dense posteriors are compared to 1e-6 absolute
-(north_star tolerance: 1e-4) and sparse membership is allowed to differ only for entries within
-1e-6 of the 0.01 cut.
+Tolerance: NONE (north_star allows 1e-4).  Forward-M, Backward-M and the total log-probability are
+IEEE add/mul in the reference's order; the posterior's expf is a restatement of glibc's algorithm
+that matches it on every float of the score range (muscle_b200/csrc/common.cuh), so dense
+posteriors, the sparse store and the EA scores are compared BIT-EXACT as well.
 """
 import os
 import numpy as np
@@ -14,7 +13,8 @@ from muscle_b200 import synth
 
 pytestmark = pytest.mark.gpu
 
-POST_TOL = 1e-6
+POST_TOL = 0.0        # bit-exact
+EA_TOL = 0.0
 
 
 def _dense_check(engine, oracle, X, Y, force_c=0):
@@ -83,12 +83,12 @@ def test_allpairs_c1_sparse_and_ea(engine, oracle):
 	ea = engine.posteriors_allpairs()
 	n = len(seqs)
 	iu = np.triu_indices(n, 1)
-	assert np.abs(ea - r["ea"][iu]).max() <= 1e-6
+	assert np.abs(ea - r["ea"][iu]).max() <= EA_TOL
 	nnz, tot = engine.store_nnz()
 	for k in range(len(nnz)):
 		off, ent = engine.export_pair(k, int(nnz[k]))
 		_sparse_equal(off, ent, r["row_off"][k], r["entries"][k], "pair %d" % k)
-	assert abs(int(tot) - int(r["nnz"].sum())) <= 4
+	assert int(tot) == int(r["nnz"].sum())
 
 
 def test_family8_golden(engine):
@@ -98,7 +98,7 @@ def test_family8_golden(engine):
 	ea = engine.posteriors_allpairs()
 	n = len(seqs)
 	iu = np.triu_indices(n, 1)
-	assert np.abs(ea - z["ea"][iu]).max() <= 1e-6
+	assert np.abs(ea - z["ea"][iu]).max() <= EA_TOL
 	nnz, _ = engine.store_nnz()
 	for k in range(len(nnz)):
 		off, ent = engine.export_pair(k, int(nnz[k]))
@@ -116,7 +116,7 @@ def test_pair_list_api_and_order(engine, oracle):
 		off_o, ent_o = oracle.sparse(p)
 		off, ent = engine.export_pair(k, int(nnz[k]))
 		_sparse_equal(off, ent, off_o, ent_o)
-		assert abs(ea[k] - oracle.alnscore(p)/min(len(seqs[x]), len(seqs[y]))) <= 1e-6
+		assert abs(ea[k] - oracle.alnscore(p)/min(len(seqs[x]), len(seqs[y]))) <= EA_TOL
 
 
 def test_errors(engine):
@@ -137,7 +137,7 @@ def test_config4_scale_long_pair(engine, oracle):
 	off, ent = engine.export_pair(0)
 	off_o, ent_o = oracle.sparse(p)
 	_sparse_equal(off, ent, off_o, ent_o, "long pair")
-	assert abs(ea[0] - oracle.alnscore(p)/min(len(X), len(Y))) <= 1e-6
+	assert abs(ea[0] - oracle.alnscore(p)/min(len(X), len(Y))) <= EA_TOL
 
 
 def test_nucleotide_alphabet(tables):
@@ -156,7 +156,7 @@ def test_nucleotide_alphabet(tables):
 		assert np.float32(tot) == k["total%d" % i]
 		assert np.abs(post - k["post%d" % i]).max() <= POST_TOL
 		ea = e.posteriors([0], [1])
-		assert abs(ea[0] - float(k["alnscore%d" % i])/min(len(X), len(Y))) <= 1e-6
+		assert abs(ea[0] - float(k["alnscore%d" % i])/min(len(X), len(Y))) <= EA_TOL
 	# tables can be swapped on a live context (the reference rewrites them between replicates)
 	e.set_hmm(tables)
 	e.close()
