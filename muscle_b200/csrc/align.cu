@@ -51,6 +51,8 @@ struct AlnProblem
 	float *score;
 	};
 
+#define ALN_VPT 4            // columns per thread and pass: one pass covers 1024 columns
+
 __global__ void __launch_bounds__(ALN_THREADS)
 k_alnflat(const AlnProblem *probs)
 	{
@@ -89,24 +91,26 @@ k_alnflat(const AlnProblem *probs)
 		__syncthreads();
 		char *tbrow = pr.tb + (size_t) i*LY1;
 		if (tid == 0)
-			{
 			tbrow[0] = 'X';                                   // calcalnflat.cpp:25
-			carry_s = 0.0f;                                   // new[0] = 0
-			}
-		__syncthreads();
-		for (uint32_t j0 = 1; j0 <= LY; j0 += ALN_THREADS)
+		float carry = 0.0f;                                   // new[0] = 0
+		for (uint32_t j0 = 1; j0 <= LY; j0 += ALN_THREADS*ALN_VPT)
 			{
-			const uint32_t j = j0 + tid;
-			const bool in = j <= LY;
-			float B = 0.0f, X = 0.0f;
-			if (in)
+			const uint32_t jb = j0 + tid*ALN_VPT;             // this thread's first column
+			float B[ALN_VPT], X[ALN_VPT], r[ALN_VPT];
+			float left = jb <= LY ? old[jb - 1] : 0.0f;
+#pragma unroll
+			for (int q = 0; q < ALN_VPT; ++q)
 				{
-				B = __fadd_rn(old[j - 1], prow[j]);
-				X = old[j];
+				const uint32_t j = jb + q;
+				const bool in = j <= LY;
+				X[q] = in ? old[j] : 0.0f;
+				B[q] = in ? __fadd_rn(left, prow[j]) : 0.0f;
+				left = X[q];
+				const float v = fmaxf(B[q], X[q]);
+				r[q] = q == 0 ? v : fmaxf(r[q > 0 ? q - 1 : 0], v);
 				}
-			float v = in ? fmaxf(B, X) : 0.0f;
-			// inclusive prefix max across the block
-			float run = v;
+			// inclusive prefix max of the per-thread maxima across the block
+			float run = r[ALN_VPT - 1];
 #pragma unroll
 			for (int o = 1; o < 32; o <<= 1)
 				{
@@ -117,31 +121,40 @@ k_alnflat(const AlnProblem *probs)
 			if (lane == 31)
 				warpmax[wid] = run;
 			__syncthreads();
-			float pre = carry_s;                              // max of everything left of this chunk
+			float pre = carry;                                // max of everything left of this pass
 			for (uint32_t w = 0; w < wid; ++w)
 				pre = fmaxf(pre, warpmax[w]);
-			float excl = __shfl_up_sync(MB_FULL, run, 1);     // new[j-1] inside the warp
+			float excl = __shfl_up_sync(MB_FULL, run, 1);     // new[jb-1] inside the warp
 			excl = lane == 0 ? pre : fmaxf(excl, pre);
-			const float nw = fmaxf(run, pre);                 // new[j]
-			__syncthreads();                                  // all reads of old[]/carry_s done
-			if (in)
+			float Y = excl;
+#pragma unroll
+			for (int q = 0; q < ALN_VPT; ++q)
 				{
-				const float Y = excl;
-				char t;
-				if (B >= X)
-					t = (B >= Y) ? 'B' : 'Y';
-				else
-					t = (X >= Y) ? 'X' : 'Y';
-				tbrow[j] = t;
+				const uint32_t j = jb + q;
+				const float nw = fmaxf(r[q], excl);               // new[j]
+				if (j <= LY)
+					{
+					char t;
+					if (B[q] >= X[q])
+						t = (B[q] >= Y) ? 'B' : 'Y';                 // best3.h:5-28 tie order
+					else
+						t = (X[q] >= Y) ? 'X' : 'Y';
+					tbrow[j] = t;
+					// old[] must stay the previous row until every thread has read it: park in prow[]
+					prow[j] = nw;
+					}
+				Y = nw;
 				}
-			if (tid == ALN_THREADS - 1)
-				carry_s = nw;
-			// old[j-1] of the NEXT chunk's first cell is old[j0+ALN_THREADS-1]: it must stay the old
-			// row until that chunk has read it, so new values are parked in prow[] and copied later
-			if (in)
-				prow[j] = nw;
-			__syncthreads();
+			if (j0 + ALN_THREADS*ALN_VPT <= LY)
+				{
+				// another pass follows: hand the running maximum over
+				if (tid == ALN_THREADS - 1)
+					carry_s = Y;
+				__syncthreads();
+				carry = carry_s;
+				}
 			}
+		__syncthreads();
 		for (uint32_t j = tid + 1; j <= LY; j += ALN_THREADS)
 			{
 			old[j] = prow[j];
