@@ -146,6 +146,18 @@ int mb200_align_groups(mb200_ctx *ctx,
 int mb200_calc_post_dense(mb200_ctx *ctx, uint32_t x, uint32_t y, float *post_out,
                           float *fwd_m_out, float *bwd_m_out, float *total_out);
 
+/* ---- test / tuning hooks (not needed by a binding) ------------------------------------------ */
+/* Residue classes of a set of PairHMM tables: bytes with the same insert score and the same match
+ * row and column share a class (21 for proteins: 20 letters, both cases, + one wildcard class).
+ * Pure host code, works without a CUDA device.  rep_out (may be NULL) gets the first byte per class. */
+int mb200_residue_classes(const float ins[256], const float match[65536], uint8_t byte2class[256],
+                          int *nclass_out, int rep_out[256]);
+/* force the columns-per-lane of mb200_calc_post_dense (0 = automatic): exercises the strip code */
+int mb200_debug_force_c(mb200_ctx *ctx, int c);
+/* expected entries per posterior row used to size the entry pool (default 12; the pool is re-sized
+ * with the exact count and the stage re-run if it was too small) */
+int mb200_set_nnz_per_row_cap(mb200_ctx *ctx, uint32_t cap);
+
 /* ---- instrumentation ---------------------------------------------------------------------- */
 typedef struct
 	{

@@ -147,26 +147,14 @@ int mb200_get_stats(const mb200_ctx *ctx, mb200_stats *out)
 	return MB200_OK;
 	}
 
-// ------------------------------------------------------------------------------------------
-// HMM tables: bytes with identical insert score and identical match row/column are merged into
-// one residue class so that the device tables stay tiny (21 classes for proteins).
-static int recode_seqs(mb200_ctx *ctx);
-
-int mb200_set_hmm(mb200_ctx *ctx, const float start[5], const float trans[25], const float ins[256],
-  const float match[65536], float min_sparse_score)
+// Pure host helper (no device needed; also exported for the CPU tests): bytes with the same insert
+// score and the same match row AND column form one residue class; class ids are assigned in order
+// of first appearance, rep[k] is the first byte of class k.
+extern "C" int mb200_residue_classes(const float ins[256], const float match[65536], uint8_t byte2class[256],
+  int *nclass_out, int rep_out[256])
 	{
-	if (!ctx || !start || !trans || !ins || !match)
-		return mb_fail(ctx, MB200_EINVAL, "mb200_set_hmm: NULL argument");
-	cudaSetDevice(ctx->device);
-	MbHmm &h = ctx->hmm;
-	// state order M=0, IX=1, IY=2, JX=3, JY=4 (pairhmm.h:11-19); aliases of hmmscores.h:1-13
-	h.tSM = start[0]; h.tSI = start[1]; h.tSJ = start[3];
-	h.tMM = trans[0*5 + 0]; h.tMI = trans[0*5 + 1]; h.tMJ = trans[0*5 + 3];
-	h.tII = trans[1*5 + 1]; h.tIM = trans[1*5 + 0];
-	h.tJJ = trans[3*5 + 3]; h.tJM = trans[3*5 + 0];
-	h.minScore = min_sparse_score;
-
-	// class of byte b = first byte a<=b with the same insert score and the same match row & column
+	if (!ins || !match || !byte2class || !nclass_out)
+		return MB200_EINVAL;
 	int nclass = 0;
 	int rep[256];
 	for (int b = 0; b < 256; ++b)
@@ -187,13 +175,39 @@ int mb200_set_hmm(mb200_ctx *ctx, const float start[5], const float trans[25], c
 			}
 		if (found < 0)
 			{
-			if (nclass >= 256)
-				return mb_fail(ctx, MB200_EALPHABET, "internal: class table overflow");
 			rep[nclass] = b;
 			found = nclass++;
 			}
-		ctx->byte2class[b] = (uint8_t) found;
+		byte2class[b] = (uint8_t) found;
 		}
+	*nclass_out = nclass;
+	if (rep_out)
+		memcpy(rep_out, rep, sizeof(int)*256);
+	return MB200_OK;
+	}
+
+// ------------------------------------------------------------------------------------------
+// HMM tables: bytes with identical insert score and identical match row/column are merged into
+// one residue class so that the device tables stay tiny (21 classes for proteins).
+static int recode_seqs(mb200_ctx *ctx);
+
+int mb200_set_hmm(mb200_ctx *ctx, const float start[5], const float trans[25], const float ins[256],
+  const float match[65536], float min_sparse_score)
+	{
+	if (!ctx || !start || !trans || !ins || !match)
+		return mb_fail(ctx, MB200_EINVAL, "mb200_set_hmm: NULL argument");
+	cudaSetDevice(ctx->device);
+	MbHmm &h = ctx->hmm;
+	// state order M=0, IX=1, IY=2, JX=3, JY=4 (pairhmm.h:11-19); aliases of hmmscores.h:1-13
+	h.tSM = start[0]; h.tSI = start[1]; h.tSJ = start[3];
+	h.tMM = trans[0*5 + 0]; h.tMI = trans[0*5 + 1]; h.tMJ = trans[0*5 + 3];
+	h.tII = trans[1*5 + 1]; h.tIM = trans[1*5 + 0];
+	h.tJJ = trans[3*5 + 3]; h.tJM = trans[3*5 + 0];
+	h.minScore = min_sparse_score;
+
+	int nclass = 0;
+	int rep[256];
+	mb200_residue_classes(ins, match, ctx->byte2class, &nclass, rep);
 	if (nclass > MB_MAX_K)
 		return mb_fail(ctx, MB200_EALPHABET, "%d distinct residue classes in the HMM tables, device tables hold %d",
 		  nclass, MB_MAX_K);

@@ -17,7 +17,8 @@ EXPORTS = [
 	"mb200_posteriors", "mb200_posteriors_allpairs", "mb200_store_npairs", "mb200_store_nnz",
 	"mb200_export_pair", "mb200_export_all", "mb200_store_pack", "mb200_store_load_allpairs",
 	"mb200_store_values", "mb200_store_set_values", "mb200_consistency_iter", "mb200_align_pairs",
-	"mb200_align_groups", "mb200_calc_post_dense", "mb200_get_stats",
+	"mb200_align_groups", "mb200_calc_post_dense", "mb200_get_stats", "mb200_residue_classes",
+	"mb200_debug_force_c", "mb200_set_nnz_per_row_cap",
 ]
 
 
