@@ -57,3 +57,32 @@ def test_mpc_pipeline_bitexact(ref, oracle):
 	s2, path2 = oracle.calcaln(mine)
 	assert np.float32(s2) == np.float32(score) and path2 == path
 	M.close()
+
+
+def test_committed_goldens_are_what_the_reference_produces(ref):
+	"""tests/golden/kat_pairs.npz and family8.npz (read on the GPU box, where /root/reference does not
+	exist) are regenerated from the compiled reference and must match the committed bytes."""
+	import os
+	from conftest import GOLDEN
+	z = np.load(os.path.join(GOLDEN, "kat_pairs.npz"))
+	for k in range(int(z["n"])):
+		X, Y = z["x%d" % k].tobytes(), z["y%d" % k].tobytes()
+		f, b = ref.fwd(X, Y), ref.bwd(X, Y)
+		assert f.tobytes() == z["fwd%d" % k].tobytes() and b.tobytes() == z["bwd%d" % k].tobytes()
+		p = ref.post(X, Y)
+		assert p.tobytes() == z["post%d" % k].tobytes()
+		sc, path = ref.calcaln(p)
+		assert np.float32(sc) == z["calcaln%d" % k] and path.encode() == z["path%d" % k].tobytes()
+	fz = np.load(os.path.join(GOLDEN, "family8.npz"))
+	seqs = [fz["seq%d" % i].tobytes() for i in range(int(fz["n"]))]
+	M = ref.mpc(seqs)
+	M.posteriors()
+	assert M.distmx().tobytes() == fz["ea"].tobytes()
+	offs, ents = M.export_all()
+	for p in range(len(offs)):
+		assert (offs[p] == fz["off%d" % p]).all() and ents[p].tobytes() == fz["ent0_%d" % p].tobytes()
+	M.consiter()
+	_, ents1 = M.export_all()
+	for p in range(len(offs)):
+		assert ents1[p].tobytes() == fz["ent1_%d" % p].tobytes()
+	M.close()
