@@ -86,3 +86,22 @@ def test_committed_goldens_are_what_the_reference_produces(ref):
 	for p in range(len(offs)):
 		assert ents1[p].tobytes() == fz["ent1_%d" % p].tobytes()
 	M.close()
+
+
+def test_random_small_pairs_bitexact(ref, oracle):
+	"""200 random pairs, lengths 1..40, alphabet with lower case, wildcards and non-letters:
+	every function of the restatement equals the compiled reference bit for bit."""
+	rng = np.random.default_rng(12345)
+	alpha = list("ACDEFGHIKLMNPQRSTVWY"*3 + "acdxBZUO*-.")
+	for _ in range(200):
+		X = "".join(rng.choice(alpha, size=int(rng.integers(1, 41))))
+		Y = "".join(rng.choice(alpha, size=int(rng.integers(1, 41))))
+		assert oracle.fwd(X, Y).tobytes() == ref.fwd(X, Y).tobytes(), (X, Y)
+		assert oracle.bwd(X, Y).tobytes() == ref.bwd(X, Y).tobytes(), (X, Y)
+		p = oracle.post(X, Y)
+		assert p.tobytes() == ref.post(X, Y).tobytes(), (X, Y)
+		o1, e1 = oracle.sparse(p)
+		o2, e2 = ref.sparse(p)
+		assert (o1 == o2).all() and e1.tobytes() == e2.tobytes()
+		assert oracle.alnscore(p) == ref.alnscore(p)
+		assert oracle.calcaln(p) == ref.calcaln(p)
