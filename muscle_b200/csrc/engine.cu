@@ -84,8 +84,6 @@ int mb200_create(int device, mb200_ctx **out)
 		return mb_fail(nullptr, MB200_EINVAL, "device %d out of range (have %d)", device, ndev);
 	ctx = new mb200_ctx();
 	ctx->device = device;
-	if (const char *kv = getenv("MB200_KERNEL"))          // "reg": register-resident k_posterior<C>; default "sm"
-		ctx->use_sm_kernel = strcmp(kv, "reg") != 0;
 	ctx->err[0] = 0;
 	if (cudaSetDevice(device) != cudaSuccess || cudaGetDeviceProperties(&ctx->prop, device) != cudaSuccess)
 		{
@@ -337,8 +335,8 @@ static int prepare_plan(mb200_ctx *ctx, int force_c)
 		{
 		const uint32_t LY = ctx->h_len[ctx->h_py[k]];
 		int C = force_c > 0 ? force_c : (int) std::min<uint32_t>(MB_MAX_C, (LY + 31)/32);
-		if (ctx->use_sm_kernel && force_c <= 0)
-			C = (C + 3)/4*4;                   // k_posterior_sm: bins only size the smem state (4, 8, 12, 16)
+		if (force_c <= 0)
+			C = (C + 3)/4*4;                   // bins only size the smem state (4, 8, 12, 16)
 		bins[C].push_back(k);
 		cost[k] = (uint64_t) ctx->h_len[ctx->h_px[k]]*LY;
 		}
@@ -410,21 +408,12 @@ static int run_posteriors(mb200_ctx *ctx, float *ea_out, const PostDebug *dbg, i
 			const uint32_t nstrips = (lymax + W - 1)/W;
 			int smem_static = 0, occ = 0;
 			size_t smem;
-			if (ctx->use_sm_kernel)
-				{
-				mb_post_sm_dispatch(2, dim3(), 0, ks, nullptr, &smem_static);
-				smem = (size_t) smem_static + (size_t)((ctx->hmm.K*ctx->hmm.KS + 3) & ~3)*sizeof(float)
-				  + (size_t) MB_WARPS_PER_BLOCK*6*C*32*sizeof(float);
-				mb_post_sm_dispatch(1, dim3(), smem, ks, nullptr, &occ);
-				}
-			else
-				{
-				mb_post_dispatch(C, 2, dim3(), 0, ks, nullptr, &smem_static);
-				smem = (size_t) smem_static + (size_t) ctx->hmm.K*ctx->hmm.KS*sizeof(float);
-				mb_post_dispatch(C, 1, dim3(), smem, ks, nullptr, &occ);
-				}
+			mb_post_sm_dispatch(2, dim3(), 0, ks, nullptr, &smem_static);
+			smem = (size_t) smem_static + (size_t)((ctx->hmm.K*ctx->hmm.KS + 3) & ~3)*sizeof(float)
+			  + (size_t) MB_WARPS_PER_BLOCK*6*C*32*sizeof(float);
+			mb_post_sm_dispatch(1, dim3(), smem, ks, nullptr, &occ);
 			if (occ <= 0)
-				return mb_fail(ctx, MB200_ECUDA, "k_posterior<%d> cannot be resident (smem %zu)", C, smem);
+				return mb_fail(ctx, MB200_ECUDA, "k_posterior_sm (CM=%d) cannot be resident (smem %zu)", C, smem);
 			uint32_t nblocks = (uint32_t) occ*ctx->prop.multiProcessorCount;
 			const uint32_t need_blocks = ((uint32_t) b.size() + MB_WARPS_PER_BLOCK - 1)/MB_WARPS_PER_BLOCK;
 			nblocks = std::max(1u, std::min(nblocks, need_blocks));
@@ -479,10 +468,7 @@ static int run_posteriors(mb200_ctx *ctx, float *ea_out, const PostDebug *dbg, i
 				P.dbg_fwd = dbg->fwd; P.dbg_bwd = dbg->bwd; P.dbg_post = dbg->post; P.dbg_total = dbg->total;
 				}
 			P.cmax = (uint32_t) C;
-			if (ctx->use_sm_kernel)
-				mb_post_sm_dispatch(0, dim3(nblocks), smem, ks, &P, nullptr);
-			else if (!mb_post_dispatch(C, 0, dim3(nblocks), smem, ks, &P, nullptr))
-				return mb_fail(ctx, MB200_EINVAL, "no kernel instance for C=%d", C);
+			mb_post_sm_dispatch(0, dim3(nblocks), smem, ks, &P, nullptr);
 			CU(cudaGetLastError());
 			ctx->stats.kernel_launches++;
 			}
@@ -522,6 +508,7 @@ static int run_posteriors(mb200_ctx *ctx, float *ea_out, const PostDebug *dbg, i
 	cudaEventElapsedTime(&ctx->stats.last_total_ms, ctx->ev0, ctx->ev3);
 	ctx->store_valid = true;
 	ctx->store_tr_valid = false;
+	ctx->store_masks_valid = false;
 	ctx->store_packed = false;
 	return MB200_OK;
 	}

@@ -42,6 +42,7 @@ struct mb200_ctx
 	bool store_packed = false;        // entries are packed in store order (entbase ascending, no holes)
 	bool store_tr_valid = false;      // transposed orientation + permutation built
 	bool tr_values_stale = false;     // forward values changed since the transposed copy was refreshed
+	bool store_masks_valid = false;   // column bit masks of both orientations built (relax.cu)
 	std::vector<uint64_t> h_tr_rowbase;
 	uint64_t store_nnz = 0;
 	uint32_t nnz_per_row_cap = 12;    // entry pool sizing guess (retry with the exact count on overflow)
@@ -56,6 +57,12 @@ struct mb200_ctx
 	DevBuf d_pack_off, d_pack_ent;    // packed image for exchange/export
 	// transposed orientation of every pair (rows = positions of Y) for the relax kernel
 	DevBuf d_tr_rowoff, d_tr_rowbase, d_tr_entries, d_tr_entbase, d_tr_perm;
+	// column bit masks of every sparse row, both orientations (relax.cu): hdr = {first word slot,
+	// w0 | nw << 16} per row, words = {mask of columns 32w..32w+31, index of the first such entry}
+	DevBuf d_mk_hdr, d_mk_words, d_tr_mk_hdr, d_tr_mk_words;
+	// relax work order (pairs of [p_lo,p_hi) in 2-D tile order) and the range it was built for
+	DevBuf d_relax_order;
+	uint32_t relax_order_n = 0, relax_order_lo = 0, relax_order_hi = 0;
 	DevBuf d_tmp, d_tmp2;
 
 	// cached launch plan of the posterior stage (depends only on the pair list)
@@ -72,11 +79,11 @@ struct mb200_ctx
 	cudaEvent_t aux_done[kStreams] = {};
 	DevBuf d_dbg;
 	int debug_force_c = 0;
-	bool use_sm_kernel = true;        // k_posterior_sm (state in smem) vs k_posterior<C> (state in registers)
 	};
 
 int mb_fail(mb200_ctx *ctx, int code, const char *fmt, ...);
 int mb_store_pack_inplace(mb200_ctx *ctx);
 int mb_store_build_transposed(mb200_ctx *ctx);
 int mb_store_refresh_transposed(mb200_ctx *ctx);
+int mb_store_build_masks(mb200_ctx *ctx);
 void mb_allpairs_list(uint32_t n, uint32_t p_lo, uint32_t p_hi, std::vector<uint32_t> &px, std::vector<uint32_t> &py);

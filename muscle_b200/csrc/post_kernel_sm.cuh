@@ -1,18 +1,34 @@
 // post_kernel_sm.cuh -- k_posterior_sm: the fused Forward -> total -> Backward+posterior -> sparsify
-// -> EA kernel with the per-lane wavefront state in SHARED MEMORY and a rolled loop over the C
-// columns a lane owns (C is a runtime value = ceil(LY/32) of the warp's current pair).
+// -> EA kernel.
 //
-// Why (profiles/r01_k_posterior_ncu_summary.md): the register-resident variant (post_kernel.cuh,
-// k_posterior<C>) unrolls C cells x ~165 instructions per direction; at C=11 the two hot loop
-// bodies are ~60 KB of SASS and ncu attributes 2.6 stall cycles per issued instruction to
-// `no_instruction` (instruction-cache misses), issue-active 54 %.  Here the hot loops are two cells
-// long (~5 KB each), every warp of every bin runs the same code, and the register footprint drops
-// so that occupancy is bounded by shared memory instead.
+// Replaces, per sequence pair, CalcFwdFlat (fwdflat3.cpp:12-153), CalcTotalProbFlat
+// (totalprobflat.cpp:3-16), CalcBwdFlat (bwdflat3.cpp:10-184), CalcPostFlat
+// (calcposteriorflat.cpp:4-27), MySparseMx::FromPost (mysparsemx.cpp:115-152) and CalcAlnScoreFlat
+// (calcalnscoreflat.cpp:4-32) of the reference.
 //
-// Same mapping, arithmetic and operation order as post_kernel.cuh (see there for the reference
-// citations): lane l owns columns l*C..l*C+C-1 of the strip, anti-diagonal wavefront over rows,
-// three shuffles per step, Forward-M spilled as [step][c][lane] (every access a full 128-byte line).
-// State arrays are indexed [c][lane] -> bank == lane, conflict free.
+// Mapping.  One warp owns one pair at a time (persistent warps pull pairs, longest first, from an
+// atomic cursor).  Lane l owns C consecutive DP columns of Y (C = ceil(LY/32), a runtime value); a
+// warp therefore covers a strip of 32*C columns and longer Y are processed strip after strip with
+// the strip-edge column handed over through a small per-warp buffer.  Rows of X are swept in
+// anti-diagonal (wavefront) order: at step t lane l works on row t-l, the cell to the left lives in
+// lane l-1 and was produced one step earlier, so the recurrence dependency is a few warp shuffles
+// per step.  The per-column wavefront state lives in SHARED MEMORY as [c][lane] arrays (bank ==
+// lane, conflict free) and the loop over the lane's columns is rolled: the hot loops are short and
+// stay in the instruction cache (the round-1 register-resident, fully unrolled variant spent 2.6
+// stall cycles per issued instruction on instruction fetch, profiles/r01_SUMMARY.md).  Only the
+// Forward M-state is spilled (4 B/cell), in [step][c][lane] order so that both the Forward write
+// and the Backward read are full 128-byte lines.  Backward walks the same anti-diagonals in
+// reverse, fuses the Fwd (*) Bwd posterior, thresholds at log(0.01) and appends survivors to a
+// per-row candidate list; the warp then compacts the rows into MySparseMx order and runs the
+// expected-accuracy max-sum DP row by row as a warp-wide prefix-max (new[j] = max_{k<=j}
+// max(old[k], old[k-1]+P[k]) is exactly the reference's max3 recurrence because every value is an
+// exact max of the same sums).
+//
+// Border handling without special code paths: LOG_ZERO is absorbing under the branch-free LogAdd,
+// so the reference's border formulas (first row/column of Forward, fwdflat3.cpp:35-93; last
+// row/column of Backward, bwdflat3.cpp:132-176) fall out of the general cell update when the
+// out-of-range neighbours are LOG_ZERO.  The only injected values are the start scores at Forward
+// (0,0) and the end scores at Backward (LX,LY) (bwdflat3.cpp:53-61).
 #pragma once
 #include "common.cuh"
 

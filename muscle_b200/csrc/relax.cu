@@ -7,13 +7,30 @@
 // Formulation.  The reference scatters P_XZ[i,k]*P_ZY[k,j] into a dense LX*LY scratch and then
 // keeps only XY's own pattern.  Here every stored entry (i,j) of XY is owned by one thread that
 // GATHERS its own sum: with both orientations of every pair in HBM, row i of S[x->z] and row j of
-// S[y->z] are two short column-sorted lists and the contribution of z is their sparse dot product
-// (a merge).  For a fixed entry the reference adds the products in ascending z and, inside one z,
-// in ascending k for all three of its loop nests; the merge visits k ascending, z runs ascending,
-// every product is one __fmul_rn and every accumulation one __fadd_rn, so the result is
-// bit-identical (verified against the oracle).  Relax is a sparse-sparse contraction (about 7
-// non-zeros per row, 2 % density): tensor cores do not apply (DESIGN.md "relax is not a GEMM").
+// S[y->z] are two short column-sorted lists and the contribution of z is their sparse dot product.
+// For a fixed entry the reference adds the products in ascending z and, inside one z, in ascending
+// k for all three of its loop nests; here z runs ascending, matches are visited k ascending, every
+// product is one __fmul_rn and every accumulation one __fadd_rn, so the result is bit-identical
+// (verified against the oracle and the compiled reference).
+//
+// Finding the matching k (round 2).  Measured on real and synthetic posteriors a sparse row holds
+// ~7 entries scattered over a span of ~55 columns (92 % of the rows are not contiguous), and a pair
+// of rows (A_i, B_j) shares only ~0.7 columns per (entry, z): the round-1 kernel spent ~15 merge
+// steps and ~30 gathered loads per (entry, z) to find them and was bound by L1 gather wavefronts
+// (profiles/r01_k_relax_ncu_raw.csv: 83 % of the L1 data pipe, 12.6/32 lanes).  The pattern of the
+// store never changes during consistency (mysparsemx.cpp:87-113), so the columns of every row, in
+// both orientations, are encoded ONCE as bit masks over 32-column words
+//      hdr[row]  = { slot of the row's first word, w0 | nw << 16 }      (w0 = first column / 32)
+//      word[s]   = { mask of columns 32(w0+t)..+31, index of the first entry of that word }
+// and a dot product becomes: intersect the two word ranges (1.6 words on average), AND the masks,
+// and for every surviving bit (ascending = k ascending) fetch the two values by popcount.  That is
+// ~6 loads and ~40 instructions per (entry, z) instead of ~30 and ~240.
+//
+// Relax is a sparse-sparse contraction (2 % density, scattered): tensor cores do not apply
+// (DESIGN.md "relax is not a GEMM").
 #include "engine.h"
+#include <cub/cub.cuh>
+#include <thrust/iterator/transform_iterator.h>
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
@@ -24,24 +41,167 @@
 #define ENSURE(buf, bytes) do { if ((buf).ensure(bytes) != 0) \
 	return mb_fail(ctx, MB200_ENOMEM, "device allocation of %zu bytes failed (%s)", (size_t)(bytes), #buf); } while (0)
 
+// ---------------------------------------------------------------------------------------------
+// column bit masks of one orientation.  Rows are addressed like the CSR offsets: slot
+// rowbase[k] + i for row i of store pair k (the slot of the sentinel offset holds an empty row).
+// One warp per pair, one lane per row.
+__global__ void k_mask_count(uint32_t npairs, const uint64_t *__restrict__ rowbase, const uint32_t *__restrict__ rowoff,
+  const uint64_t *__restrict__ entbase, const mb200_entry *__restrict__ entries, uint32_t *__restrict__ nw_out)
+	{
+	const uint32_t warp = (blockIdx.x*blockDim.x + threadIdx.x) >> 5;
+	const uint32_t lane = threadIdx.x & 31;
+	const uint32_t nwarps = (gridDim.x*blockDim.x) >> 5;
+	for (uint32_t k = warp; k < npairs; k += nwarps)
+		{
+		const uint64_t rb = rowbase[k];
+		const uint32_t nrow = (uint32_t)(rowbase[k + 1] - rb) - 1;
+		const uint32_t *ro = rowoff + rb;
+		const mb200_entry *en = entries + entbase[k];
+		for (uint32_t i = lane; i <= nrow; i += 32)
+			{
+			uint32_t nw = 0;
+			if (i < nrow)
+				{
+				const uint32_t a = ro[i], b = ro[i + 1];
+				if (b > a)
+					nw = (en[b - 1].col >> 5) - (en[a].col >> 5) + 1;
+				}
+			nw_out[rb + i] = nw;
+			}
+		}
+	}
+
+__global__ void k_mask_fill(uint32_t npairs, const uint64_t *__restrict__ rowbase, const uint32_t *__restrict__ rowoff,
+  const uint64_t *__restrict__ entbase, const mb200_entry *__restrict__ entries, const uint32_t *__restrict__ nw_in,
+  const uint64_t *__restrict__ wslot, uint2 *__restrict__ hdr, uint2 *__restrict__ words)
+	{
+	const uint32_t warp = (blockIdx.x*blockDim.x + threadIdx.x) >> 5;
+	const uint32_t lane = threadIdx.x & 31;
+	const uint32_t nwarps = (gridDim.x*blockDim.x) >> 5;
+	for (uint32_t k = warp; k < npairs; k += nwarps)
+		{
+		const uint64_t rb = rowbase[k];
+		const uint32_t nrow = (uint32_t)(rowbase[k + 1] - rb) - 1;
+		const uint32_t *ro = rowoff + rb;
+		const mb200_entry *en = entries + entbase[k];
+		for (uint32_t i = lane; i <= nrow; i += 32)
+			{
+			const uint32_t nw = nw_in[rb + i];
+			const uint32_t slot = (uint32_t) wslot[rb + i];
+			uint32_t w0 = 0;
+			if (nw > 0)
+				{
+				const uint32_t a = ro[i], b = ro[i + 1];
+				w0 = en[a].col >> 5;
+				uint32_t cur = w0, mask = 0, first = a;
+				for (uint32_t e = a; e < b; ++e)
+					{
+					const uint32_t c = en[e].col;
+					const uint32_t w = c >> 5;
+					if (w != cur)
+						{
+						words[slot + (cur - w0)] = make_uint2(mask, first);
+						for (uint32_t t = cur + 1; t < w; ++t)
+							words[slot + (t - w0)] = make_uint2(0u, e);
+						cur = w; mask = 0; first = e;
+						}
+					mask |= 1u << (c & 31);
+					}
+				words[slot + (cur - w0)] = make_uint2(mask, first);
+				}
+			hdr[rb + i] = make_uint2(slot, w0 | (nw << 16));
+			}
+		}
+	}
+
+struct WidenU32
+	{
+	__host__ __device__ uint64_t operator()(uint32_t v) const { return v; }
+	};
+
+static int build_masks_one(mb200_ctx *ctx, uint32_t np, uint64_t nslots, const uint64_t *rowbase, const uint32_t *rowoff,
+  const mb200_entry *entries, DevBuf &d_hdr, DevBuf &d_words)
+	{
+	cudaStream_t st = ctx->stream;
+	const int blocks = ctx->prop.multiProcessorCount*8;
+	// d_tmp: nw per slot (u32); d_tmp2: exclusive scan (u64 per slot) followed by the cub scratch
+	ENSURE(ctx->d_tmp, nslots*sizeof(uint32_t) + 64);
+	uint32_t *d_nw = (uint32_t *) ctx->d_tmp.p;
+	// 64-bit running sum of the 32-bit counts
+	auto in64 = thrust::make_transform_iterator((const uint32_t *) d_nw, WidenU32());
+	size_t tb = 0;
+	cub::DeviceScan::ExclusiveSum(nullptr, tb, in64, (uint64_t *) nullptr, (int64_t) nslots, st);
+	const size_t scan_bytes = (nslots*sizeof(uint64_t) + 255)/256*256;
+	ENSURE(ctx->d_tmp2, scan_bytes + tb + 64);
+	uint64_t *d_slot = (uint64_t *) ctx->d_tmp2.p;
+	void *d_scratch = (char *) ctx->d_tmp2.p + scan_bytes;
+	k_mask_count<<<blocks, 256, 0, st>>>(np, rowbase, rowoff, (const uint64_t *) ctx->d_entbase.p, entries, d_nw);
+	CU(cudaGetLastError());
+	cub::DeviceScan::ExclusiveSum(d_scratch, tb, in64, d_slot, (int64_t) nslots, st);
+	CU(cudaGetLastError());
+	uint64_t last_slot = 0;
+	uint32_t last_nw = 0;
+	CU(cudaMemcpyAsync(&last_slot, d_slot + (nslots - 1), sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+	CU(cudaMemcpyAsync(&last_nw, d_nw + (nslots - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+	CU(cudaStreamSynchronize(st));
+	const uint64_t nwords = last_slot + last_nw;
+	if (nwords >= 0xffffffffull)
+		return mb_fail(ctx, MB200_EOVERFLOW, "column masks need %llu words (32-bit slots)", (unsigned long long) nwords);
+	ENSURE(d_hdr, nslots*sizeof(uint2));
+	ENSURE(d_words, (nwords + 8)*sizeof(uint2));
+	k_mask_fill<<<blocks, 256, 0, st>>>(np, rowbase, rowoff, (const uint64_t *) ctx->d_entbase.p, entries, d_nw, d_slot,
+	  (uint2 *) d_hdr.p, (uint2 *) d_words.p);
+	CU(cudaGetLastError());
+	ctx->stats.kernel_launches += 3;
+	return MB200_OK;
+	}
+
+int mb_store_build_masks(mb200_ctx *ctx)
+	{
+	int rc = mb_store_build_transposed(ctx);
+	if (rc != MB200_OK)
+		return rc;
+	if (ctx->store_masks_valid)
+		return MB200_OK;
+	const uint32_t np = (uint32_t) ctx->h_px.size();
+	rc = build_masks_one(ctx, np, ctx->h_rowbase.back(), (const uint64_t *) ctx->d_rowbase.p, (const uint32_t *) ctx->d_rowoff.p,
+	  (const mb200_entry *) ctx->d_entries.p, ctx->d_mk_hdr, ctx->d_mk_words);
+	if (rc != MB200_OK)
+		return rc;
+	rc = build_masks_one(ctx, np, ctx->h_tr_rowbase.back(), (const uint64_t *) ctx->d_tr_rowbase.p,
+	  (const uint32_t *) ctx->d_tr_rowoff.p, (const mb200_entry *) ctx->d_tr_entries.p, ctx->d_tr_mk_hdr, ctx->d_tr_mk_words);
+	if (rc != MB200_OK)
+		return rc;
+	CU(cudaStreamSynchronize(ctx->stream));
+	ctx->store_masks_valid = true;
+	return MB200_OK;
+	}
+
+// ---------------------------------------------------------------------------------------------
 struct RelaxParams
 	{
 	uint32_t n;                       // sequences
-	uint32_t p_lo, p_hi;              // pairs to update
+	uint32_t nwork;                   // pairs to update
+	const uint32_t *order;            // work list: all-pairs indexes in 2-D tile order
 	const uint32_t *seqlen;
 	const uint64_t *rowbase;  const uint32_t *rowoff;  const mb200_entry *entries;      // forward
-	const uint64_t *trbase;   const uint32_t *troff;   const mb200_entry *trentries;    // transposed
+	const uint64_t *trbase;   const mb200_entry *trentries;                             // transposed
+	const uint2 *hdr, *words, *trhdr, *trwords;                                         // column masks
 	const uint64_t *entbase;
 	mb200_entry *out;                 // new values (same layout as entries)
 	};
 
-struct ZDesc { const uint32_t *roA; const mb200_entry *enA; const uint32_t *roB; const mb200_entry *enB; };
+// operands of one z: S[x->z] (rows = positions of x) and S[y->z] (rows = positions of y)
+struct ZDesc
+	{
+	const uint2 *hdrA, *wordsA; const mb200_entry *enA;
+	const uint2 *hdrB, *wordsB; const mb200_entry *enB;
+	};
 
 #define RELAX_THREADS 256
 #define RELAX_ZCHUNK 64
+#ifndef RELAX_EPT
 #define RELAX_EPT 4          // entries per thread held in registers per sweep
-#ifndef RELAX_BAND_GUESS
-#define RELAX_BAND_GUESS 0      // measured on C2: merge 285 ms, band-guess lookup 440 ms per iteration
 #endif
 
 __device__ __forceinline__ uint32_t pair_index(uint32_t n, uint32_t a, uint32_t b)
@@ -54,9 +214,9 @@ __global__ void __launch_bounds__(RELAX_THREADS)
 k_relax(const RelaxParams P)
 	{
 	__shared__ ZDesc zd[RELAX_ZCHUNK];
-	const uint32_t p = P.p_lo + blockIdx.x;
-	if (p >= P.p_hi)
+	if (blockIdx.x >= P.nwork)
 		return;
+	const uint32_t p = P.order[blockIdx.x];
 	// invert p -> (x,y): find x with base(x) <= p < base(x+1)
 	const uint32_t n = P.n;
 	uint32_t x = 0;
@@ -112,30 +272,31 @@ k_relax(const RelaxParams P)
 			if (threadIdx.x < RELAX_ZCHUNK)
 				{
 				const uint32_t z = z0 + threadIdx.x;
-				ZDesc d = { nullptr, nullptr, nullptr, nullptr };
+				ZDesc d;
+				d.hdrA = nullptr;
 				if (z < n && z != x && z != y)
 					{
 					// S[x->z]: rows are positions of x
 					if (x < z)
 						{
 						const uint32_t q = pair_index(n, x, z);
-						d.roA = P.rowoff + P.rowbase[q]; d.enA = P.entries + P.entbase[q];
+						d.hdrA = P.hdr + P.rowbase[q]; d.wordsA = P.words; d.enA = P.entries + P.entbase[q];
 						}
 					else
 						{
 						const uint32_t q = pair_index(n, z, x);
-						d.roA = P.troff + P.trbase[q]; d.enA = P.trentries + P.entbase[q];
+						d.hdrA = P.trhdr + P.trbase[q]; d.wordsA = P.trwords; d.enA = P.trentries + P.entbase[q];
 						}
 					// S[y->z]: rows are positions of y
 					if (y < z)
 						{
 						const uint32_t q = pair_index(n, y, z);
-						d.roB = P.rowoff + P.rowbase[q]; d.enB = P.entries + P.entbase[q];
+						d.hdrB = P.hdr + P.rowbase[q]; d.wordsB = P.words; d.enB = P.entries + P.entbase[q];
 						}
 					else
 						{
 						const uint32_t q = pair_index(n, z, y);
-						d.roB = P.troff + P.trbase[q]; d.enB = P.trentries + P.entbase[q];
+						d.hdrB = P.trhdr + P.trbase[q]; d.wordsB = P.trwords; d.enB = P.trentries + P.entbase[q];
 						}
 					}
 				zd[threadIdx.x] = d;
@@ -145,58 +306,33 @@ k_relax(const RelaxParams P)
 			for (uint32_t zz = 0; zz < zn; ++zz)
 				{
 				const ZDesc d = zd[zz];
-				if (d.roA == nullptr)
+				if (d.hdrA == nullptr)
 					continue;
 #pragma unroll
 				for (int q = 0; q < RELAX_EPT; ++q)
 					{
 					if (!live[q])
 						continue;
-					uint32_t a = d.roA[ei[q]];
-					const uint32_t aend = d.roA[ei[q] + 1];
-					const uint32_t b0 = d.roB[ej[q]];
-					const uint32_t bend = d.roB[ej[q] + 1];
-					if (a == aend || b0 == bend)
-						continue;
+					const uint2 hA = d.hdrA[ei[q]];
+					const uint2 hB = d.hdrB[ej[q]];
+					const uint32_t w0A = hA.y & 0xffffu, w0B = hB.y & 0xffffu;
+					const uint32_t lo = max(w0A, w0B);
+					const uint32_t hi = min(w0A + (hA.y >> 16), w0B + (hB.y >> 16));
 					float s = acc[q];
-#if RELAX_BAND_GUESS
-					// posterior rows are (nearly) contiguous column bands: the entry with column k sits at
-					// index k-firstcol unless the row has holes below k (then walk back a few slots)
-					const uint32_t kb0 = d.enB[b0].col;
-					for (; a < aend; ++a)
+					for (uint32_t w = lo; w < hi; ++w)
 						{
-						const mb200_entry ea = d.enA[a];
-						if (ea.col < kb0)
-							continue;
-						uint32_t idx = min(b0 + (ea.col - kb0), bend - 1);
-						mb200_entry eb2 = d.enB[idx];
-						while (eb2.col > ea.col && idx > b0)
-							eb2 = d.enB[--idx];
-						if (eb2.col == ea.col)
-							s = __fadd_rn(s, __fmul_rn(ea.p, eb2.p));      // relaxflat.cpp:27,56,90
+						const uint2 a = d.wordsA[hA.x + (w - w0A)];
+						const uint2 b = d.wordsB[hB.x + (w - w0B)];
+						uint32_t m = a.x & b.x;
+						while (m)
+							{
+							const uint32_t below = (m & (0u - m)) - 1u;       // bits under the lowest common column
+							const float pa = d.enA[a.y + __popc(a.x & below)].p;
+							const float pb = d.enB[b.y + __popc(b.x & below)].p;
+							s = __fadd_rn(s, __fmul_rn(pa, pb));               // relaxflat.cpp:27,56,90
+							m &= m - 1u;
+							}
 						}
-#else
-					// branch-free merge step: both cursors advance by predicate, the product is added only on
-					// a column match (lanes stay converged inside the loop; profiles: the 3-way if/else of the
-					// textbook merge ran at 12.6/32 active lanes)
-					uint32_t b = b0;
-					mb200_entry ea = d.enA[a], ebv = d.enB[b];
-					for (;;)
-						{
-						const bool adva = ea.col <= ebv.col;
-						const bool advb = ebv.col <= ea.col;
-						if (adva && advb)
-							s = __fadd_rn(s, __fmul_rn(ea.p, ebv.p));      // relaxflat.cpp:27,56,90
-						a += adva ? 1u : 0u;
-						b += advb ? 1u : 0u;
-						if (a >= aend || b >= bend)
-							break;
-						if (adva)
-							ea = d.enA[a];
-						if (advb)
-							ebv = d.enB[b];
-						}
-#endif
 					acc[q] = s;
 					}
 				}
@@ -223,6 +359,38 @@ __global__ void k_copy_entries(uint64_t lo, uint64_t hi, const mb200_entry *__re
 		dst[k] = src[k];
 	}
 
+// Work order of the pairs of [p_lo,p_hi): 2-D tiles of the (x,y) triangle.  Every CTA streams
+// S[x->z] and S[y->z] over all z; CTAs that are resident together start at z=0 and advance at about
+// the same pace, so when they cover a compact tile of T x T pairs the 2T operand sequences of the
+// current z are read from HBM once and then hit in the 126 MB L2 (row-major order would share x only).
+#define RELAX_TILE 16
+static int prepare_relax_order(mb200_ctx *ctx, uint32_t p_lo, uint32_t p_hi)
+	{
+	const uint32_t n = ctx->nseq;
+	if (ctx->relax_order_n == n && ctx->relax_order_lo == p_lo && ctx->relax_order_hi == p_hi && ctx->d_relax_order.p)
+		return MB200_OK;
+	std::vector<uint32_t> order;
+	order.reserve(p_hi - p_lo);
+	const uint32_t T = RELAX_TILE;
+	for (uint32_t tx = 0; tx < n; tx += T)
+		for (uint32_t ty = tx; ty < n; ty += T)
+			for (uint32_t x = tx; x < std::min(n, tx + T); ++x)
+				for (uint32_t y = std::max(ty, x + 1); y < std::min(n, ty + T); ++y)
+					{
+					const uint32_t p = (uint32_t)((uint64_t) x*n - (uint64_t) x*(x + 1)/2 + (y - x - 1));
+					if (p >= p_lo && p < p_hi)
+						order.push_back(p);
+					}
+	if (order.size() != (size_t)(p_hi - p_lo))
+		return mb_fail(ctx, MB200_EINVAL, "relax work order covers %zu of %u pairs", order.size(), p_hi - p_lo);
+	ENSURE(ctx->d_relax_order, order.size()*sizeof(uint32_t));
+	CU(cudaMemcpyAsync(ctx->d_relax_order.p, order.data(), order.size()*sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+	CU(cudaStreamSynchronize(ctx->stream));
+	ctx->stats.h2d_bytes += order.size()*sizeof(uint32_t);
+	ctx->relax_order_n = n; ctx->relax_order_lo = p_lo; ctx->relax_order_hi = p_hi;
+	return MB200_OK;
+	}
+
 extern "C" {
 
 int mb200_consistency_iter(mb200_ctx *ctx, uint32_t p_lo, uint32_t p_hi)
@@ -236,12 +404,12 @@ int mb200_consistency_iter(mb200_ctx *ctx, uint32_t p_lo, uint32_t p_hi)
 	const uint32_t np = (uint32_t) ctx->h_px.size();
 	if (p_lo > p_hi || p_hi > np)
 		return mb_fail(ctx, MB200_EINVAL, "pair range [%u,%u) invalid", p_lo, p_hi);
-	if (n < 3 || p_lo == p_hi)
+	if (n < 3)
 		return MB200_OK;                       // MPCFlat::Consistency skips N<3 (mpcflat.cpp:176)
 	cudaSetDevice(ctx->device);
 	cudaStream_t st = ctx->stream;
 	CU(cudaEventRecord(ctx->ev0, st));
-	int rc = mb_store_build_transposed(ctx);
+	int rc = mb_store_build_masks(ctx);        // packs, builds the transposed orientation and the masks once
 	if (rc != MB200_OK)
 		return rc;
 	if (ctx->tr_values_stale)
@@ -252,24 +420,33 @@ int mb200_consistency_iter(mb200_ctx *ctx, uint32_t p_lo, uint32_t p_hi)
 		ctx->tr_values_stale = false;
 		}
 	ENSURE(ctx->d_entries2, (ctx->store_nnz + 64)*sizeof(mb200_entry));
-	RelaxParams P;
-	P.n = n; P.p_lo = p_lo; P.p_hi = p_hi;
-	P.seqlen = (const uint32_t *) ctx->d_seqlen.p;
-	P.rowbase = (const uint64_t *) ctx->d_rowbase.p;
-	P.rowoff = (const uint32_t *) ctx->d_rowoff.p;
-	P.entries = (const mb200_entry *) ctx->d_entries.p;
-	P.trbase = (const uint64_t *) ctx->d_tr_rowbase.p;
-	P.troff = (const uint32_t *) ctx->d_tr_rowoff.p;
-	P.trentries = (const mb200_entry *) ctx->d_tr_entries.p;
-	P.entbase = (const uint64_t *) ctx->d_entbase.p;
-	P.out = (mb200_entry *) ctx->d_entries2.p;
 	CU(cudaEventRecord(ctx->ev1, st));
-	k_relax<<<p_hi - p_lo, RELAX_THREADS, 0, st>>>(P);
-	CU(cudaGetLastError());
-	ctx->stats.kernel_launches++;
+	if (p_hi > p_lo)
+		{
+		rc = prepare_relax_order(ctx, p_lo, p_hi);
+		if (rc != MB200_OK)
+			return rc;
+		RelaxParams P;
+		P.n = n; P.nwork = p_hi - p_lo;
+		P.order = (const uint32_t *) ctx->d_relax_order.p;
+		P.seqlen = (const uint32_t *) ctx->d_seqlen.p;
+		P.rowbase = (const uint64_t *) ctx->d_rowbase.p;
+		P.rowoff = (const uint32_t *) ctx->d_rowoff.p;
+		P.entries = (const mb200_entry *) ctx->d_entries.p;
+		P.trbase = (const uint64_t *) ctx->d_tr_rowbase.p;
+		P.trentries = (const mb200_entry *) ctx->d_tr_entries.p;
+		P.hdr = (const uint2 *) ctx->d_mk_hdr.p; P.words = (const uint2 *) ctx->d_mk_words.p;
+		P.trhdr = (const uint2 *) ctx->d_tr_mk_hdr.p; P.trwords = (const uint2 *) ctx->d_tr_mk_words.p;
+		P.entbase = (const uint64_t *) ctx->d_entbase.p;
+		P.out = (mb200_entry *) ctx->d_entries2.p;
+		CU(cudaEventRecord(ctx->ev1, st));
+		k_relax<<<p_hi - p_lo, RELAX_THREADS, 0, st>>>(P);
+		CU(cudaGetLastError());
+		ctx->stats.kernel_launches++;
+		}
 	CU(cudaEventRecord(ctx->ev2, st));
 	// pairs outside the range keep their old values until the peers' results arrive
-	const uint64_t e_lo = ctx->h_entbase[p_lo];
+	const uint64_t e_lo = p_lo < np ? ctx->h_entbase[p_lo] : ctx->store_nnz;
 	const uint64_t e_hi = p_hi < np ? ctx->h_entbase[p_hi] : ctx->store_nnz;
 	const int blocks = ctx->prop.multiProcessorCount*8;
 	if (e_lo > 0)
@@ -283,11 +460,10 @@ int mb200_consistency_iter(mb200_ctx *ctx, uint32_t p_lo, uint32_t p_hi)
 		ctx->stats.kernel_launches++;
 		}
 	CU(cudaGetLastError());
+	CU(cudaEventRecord(ctx->ev3, st));
 	CU(cudaStreamSynchronize(st));
 	std::swap(ctx->d_entries, ctx->d_entries2);            // consflat.cpp:22
 	ctx->tr_values_stale = true;
-	CU(cudaEventRecord(ctx->ev3, st));
-	CU(cudaStreamSynchronize(st));
 	cudaEventElapsedTime(&ctx->stats.last_kernel_ms, ctx->ev1, ctx->ev2);
 	cudaEventElapsedTime(&ctx->stats.last_total_ms, ctx->ev0, ctx->ev3);
 	return MB200_OK;

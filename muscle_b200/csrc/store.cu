@@ -194,6 +194,7 @@ int mb_store_pack_inplace(mb200_ctx *ctx)
 	ctx->store_nnz = total;
 	ctx->store_packed = true;
 	ctx->store_tr_valid = false;
+	ctx->store_masks_valid = false;
 	return MB200_OK;
 	}
 
@@ -338,6 +339,7 @@ int mb200_store_load_allpairs(mb200_ctx *ctx, uint32_t p_lo, uint32_t p_hi, cons
 	ctx->store_valid = true;
 	ctx->store_packed = true;
 	ctx->store_tr_valid = false;
+	ctx->store_masks_valid = false;
 	ctx->store_allpairs = (p_lo == 0 && p_hi == all);
 	ctx->plan_is_allpairs = false;
 	ctx->store_p_lo = p_lo;
