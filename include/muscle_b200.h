@@ -104,6 +104,19 @@ int mb200_store_pack(mb200_ctx *ctx, const uint32_t **d_offsets, uint64_t *n_off
 int mb200_store_load_allpairs(mb200_ctx *ctx, uint32_t p_lo, uint32_t p_hi,
                               const uint32_t *d_offsets, uint64_t n_offsets,
                               const mb200_entry *d_entries, uint64_t n_entries);
+/* In-place variant for the NCCL all-gather-v: _begin returns library-owned
+ * device buffers sized for the image of ALL N(N-1)/2 pairs (n_offsets = sum over pairs of LX+1,
+ * n_entries = total nnz); the caller's collective receives every rank's packed image (its own
+ * included, read from mb200_store_pack) directly at its final position, in pair order; _commit
+ * adopts the buffers as the store.  The rank's own packed store stays readable until _commit. */
+int mb200_store_exchange_begin(mb200_ctx *ctx, uint64_t n_offsets, uint64_t n_entries,
+                               uint32_t **d_offsets, mb200_entry **d_entries);
+int mb200_store_exchange_commit(mb200_ctx *ctx);
+/* Device pointer of the packed entries (store order).  Between consistency iterations the ranks
+ * all-gather their updated entry ranges in place through this pointer (the pattern is invariant,
+ * mysparsemx.cpp:87-113) and then call mb200_store_values_changed. */
+int mb200_store_entries_ptr(mb200_ctx *ctx, mb200_entry **d_entries, uint64_t *n_entries);
+int mb200_store_values_changed(mb200_ctx *ctx);
 /* values-only image (float per entry, store order) for the exchange between consistency
  * iterations: the pattern is invariant (mysparsemx.cpp:87-113). */
 int mb200_store_values(mb200_ctx *ctx, float *d_values_out, uint64_t n_entries);
@@ -157,6 +170,40 @@ int mb200_debug_force_c(mb200_ctx *ctx, int c);
 /* expected entries per posterior row used to size the entry pool (default 12; the pool is re-sized
  * with the exact count and the stage re-run if it was too small) */
 int mb200_set_nnz_per_row_cap(mb200_ctx *ctx, uint32_t cap);
+
+/* ---- several GPUs from one process ("mb200_create(ndev, ...)") -------- */
+/* A group is ndev single-device contexts plus the two exchange steps of the path (section 8e).
+ * It serves the single-process caller (`muscle_b200 -align`): mb200_group_posteriors_allpairs
+ * replaces MPCFlat::CalcPosteriors (mpcflat.cpp:214-252) with the pair list sharded in contiguous
+ * cell-balanced ranges and an all-gather-v of the packed store images over NVLink peer memory, so
+ * that every device ends with the complete store; mb200_group_consistency_iter replaces
+ * MPCFlat::ConsIter (consflat.cpp:5-23) with every device updating its own pair range followed by an
+ * in-place exchange of the updated entries.  The serial stages (mb200_align_groups, mb200_msa_*)
+ * run on mb200_group_ctx(g, 0).  devices == NULL or ndev <= 0: all visible devices. */
+typedef struct mb200_group mb200_group;
+int         mb200_group_create(int ndev, const int *devices, mb200_group **out);
+void        mb200_group_destroy(mb200_group *g);
+const char *mb200_group_last_error(const mb200_group *g);
+int         mb200_group_size(const mb200_group *g);
+mb200_ctx  *mb200_group_ctx(mb200_group *g, int rank);
+int mb200_group_set_hmm(mb200_group *g, const float start[5], const float trans[25],
+                        const float ins[256], const float match[65536], float min_sparse_score);
+int mb200_group_set_seqs(mb200_group *g, uint32_t nseq, const uint8_t *bytes, const uint64_t *offsets);
+int mb200_group_posteriors_allpairs(mb200_group *g, float *ea_out);   /* ea_out[N(N-1)/2], may be NULL */
+int mb200_group_consistency_iter(mb200_group *g);
+typedef struct
+	{
+	uint32_t ndev;
+	uint64_t cells;                    /* DP cells of the last posterior stage, all devices        */
+	float    posterior_ms;             /* host wall, slowest device                                */
+	float    exchange1_ms;             /* store all-gather-v                                       */
+	uint64_t exchange1_bytes_per_dev;  /* bytes every device received                              */
+	float    relax_ms;                 /* last consistency iteration, slowest device (host wall)   */
+	float    relax_kernel_ms;          /* k_relax device time, slowest device                      */
+	float    exchange2_ms;             /* in-place exchange of the updated entries                 */
+	uint64_t exchange2_bytes_per_dev;
+	} mb200_group_stats;
+int mb200_group_get_stats(const mb200_group *g, mb200_group_stats *out);
 
 /* ---- instrumentation ---------------------------------------------------------------------- */
 typedef struct

@@ -92,6 +92,7 @@ int mb200_create(int device, mb200_ctx **out)
 		return MB200_ECUDA;
 		}
 	cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+	cudaHostAlloc((void **) &ctx->h_pinned, 64*sizeof(uint32_t), cudaHostAllocDefault);
 	cudaEventCreate(&ctx->ev0);
 	cudaEventCreate(&ctx->ev1);
 	cudaEventCreate(&ctx->ev2);
@@ -112,11 +113,14 @@ void mb200_destroy(mb200_ctx *ctx)
 	cudaSetDevice(ctx->device);
 	cudaStreamSynchronize(ctx->stream);
 	DevBuf *bufs[] = { &ctx->d_matchT, &ctx->d_insT, &ctx->d_codes, &ctx->d_seqoff, &ctx->d_seqlen, &ctx->d_px,
-	  &ctx->d_py, &ctx->d_order, &ctx->d_counters,
+	  &ctx->d_py, &ctx->d_order,
 	  &ctx->d_rowoff, &ctx->d_rowbase, &ctx->d_entries, &ctx->d_cursor, &ctx->d_entbase, &ctx->d_nnz,
-	  &ctx->d_ea, &ctx->d_err, &ctx->d_dbg, &ctx->d_pack_off, &ctx->d_pack_ent, &ctx->d_entries2,
+	  &ctx->d_ea, &ctx->d_dbg, &ctx->d_pack_off, &ctx->d_pack_ent, &ctx->d_entries2,
 	  &ctx->d_tr_rowoff, &ctx->d_tr_rowbase, &ctx->d_tr_entries, &ctx->d_tr_entbase, &ctx->d_tr_perm,
-	  &ctx->d_tmp, &ctx->d_tmp2 };
+	  &ctx->d_tmp, &ctx->d_tmp2, &ctx->d_mk_hdr, &ctx->d_mk_words, &ctx->d_tr_mk_hdr, &ctx->d_tr_mk_words,
+	  &ctx->d_relax_order, &ctx->d_p2c, &ctx->d_join, &ctx->d_stage };
+	if (ctx->h_pinned)
+		cudaFreeHost(ctx->h_pinned);
 	for (DevBuf *b : bufs)
 		b->release();
 	for (int c = 0; c <= MB_MAX_C; ++c)
@@ -248,18 +252,20 @@ int mb200_set_seqs(mb200_ctx *ctx, uint32_t nseq, const uint8_t *bytes, const ui
 	if (!ctx || !bytes || !offsets || nseq == 0)
 		return mb_fail(ctx, MB200_EINVAL, "mb200_set_seqs: bad argument");
 	cudaSetDevice(ctx->device);
-	ctx->nseq = nseq;
-	ctx->h_off.assign(offsets, offsets + nseq + 1);
-	ctx->h_len.resize(nseq);
+	// validate before touching the context (a failed call leaves the previous sequences usable)
 	for (uint32_t i = 0; i < nseq; ++i)
 		{
 		if (offsets[i + 1] <= offsets[i])
 			return mb_fail(ctx, MB200_EINVAL, "sequence %u is empty or offsets not increasing", i);
-		const uint64_t L = offsets[i + 1] - offsets[i];
-		if (L > 0x7fffffffull)
+		if (offsets[i + 1] - offsets[i] > 0x7fffffffull)
 			return mb_fail(ctx, MB200_EOVERFLOW, "sequence %u too long", i);
-		ctx->h_len[i] = (uint32_t) L;
 		}
+	ctx->nseq = nseq;
+	ctx->h_off.assign(offsets, offsets + nseq + 1);
+	ctx->h_len.resize(nseq);
+	for (uint32_t i = 0; i < nseq; ++i)
+		ctx->h_len[i] = (uint32_t)(offsets[i + 1] - offsets[i]);
+	ctx->msa_valid = false;
 	ctx->h_bytes.assign(bytes + offsets[0], bytes + offsets[nseq]);
 	const uint64_t o0 = offsets[0];
 	for (auto &o : ctx->h_off)
@@ -319,9 +325,9 @@ static int prepare_plan(mb200_ctx *ctx, int force_c)
 	ENSURE(ctx->d_nnz, np*sizeof(uint32_t));
 	ENSURE(ctx->d_ea, np*sizeof(float));
 	ENSURE(ctx->d_order, np*sizeof(uint32_t));
-	ENSURE(ctx->d_counters, (MB_MAX_C + 1)*sizeof(uint32_t));
-	ENSURE(ctx->d_cursor, sizeof(unsigned long long));
-	ENSURE(ctx->d_err, sizeof(int));
+	// one control block = { entry cursor u64, error flag i32, pad, work cursors u32[MB_MAX_C+1] }:
+	// a single memset per step and a single 16-byte read-back
+	ENSURE(ctx->d_cursor, 16 + (MB_MAX_C + 1)*sizeof(uint32_t));
 	CU(cudaMemcpyAsync(ctx->d_px.p, ctx->h_px.data(), np*sizeof(uint32_t), cudaMemcpyHostToDevice, st));
 	CU(cudaMemcpyAsync(ctx->d_py.p, ctx->h_py.data(), np*sizeof(uint32_t), cudaMemcpyHostToDevice, st));
 	CU(cudaMemcpyAsync(ctx->d_rowbase.p, rowbase.data(), (np + 1)*sizeof(uint64_t), cudaMemcpyHostToDevice, st));
@@ -385,17 +391,17 @@ static int run_posteriors(mb200_ctx *ctx, float *ea_out, const PostDebug *dbg, i
 	const auto &bins = ctx->plan_bins;
 	const auto &bin_start = ctx->plan_bin_start;
 
+	bool done = false;
 	for (int attempt = 0; attempt < 3; ++attempt)
 		{
 		ENSURE(ctx->d_entries, (est_entries + 64)*sizeof(mb200_entry));
-		CU(cudaMemsetAsync(ctx->d_cursor.p, 0, sizeof(unsigned long long), st));
-		CU(cudaMemsetAsync(ctx->d_counters.p, 0, (MB_MAX_C + 1)*sizeof(uint32_t), st));
-		CU(cudaMemsetAsync(ctx->d_err.p, 0, sizeof(int), st));
+		CU(cudaMemsetAsync(ctx->d_cursor.p, 0, 16 + (MB_MAX_C + 1)*sizeof(uint32_t), st));
 		CU(cudaEventRecord(ctx->ev1, st));
 		for (int k = 0; k < mb200_ctx::kStreams; ++k)
 			CU(cudaStreamWaitEvent(ctx->aux[k], ctx->ev1, 0));
 		// widest bins first: they hold most of the work, the narrow ones fill the tails
 		int nlaunched = 0;
+		size_t free_b = 0, total_b = 0;
 		for (int C = MB_MAX_C; C >= 1; --C)
 			{
 			const auto &b = bins[C];
@@ -411,7 +417,17 @@ static int run_posteriors(mb200_ctx *ctx, float *ea_out, const PostDebug *dbg, i
 			mb_post_sm_dispatch(2, dim3(), 0, ks, nullptr, &smem_static);
 			smem = (size_t) smem_static + (size_t)((ctx->hmm.K*ctx->hmm.KS + 3) & ~3)*sizeof(float)
 			  + (size_t) MB_WARPS_PER_BLOCK*6*C*32*sizeof(float);
-			mb_post_sm_dispatch(1, dim3(), smem, ks, nullptr, &occ);
+			if (ctx->occ_cache_k != ctx->hmm.K*ctx->hmm.KS)
+				{
+				memset(ctx->occ_cache, 0, sizeof ctx->occ_cache);
+				ctx->occ_cache_k = ctx->hmm.K*ctx->hmm.KS;
+				}
+			if (ctx->occ_cache[C] == 0)
+				{
+				mb_post_sm_dispatch(1, dim3(), smem, ks, nullptr, &occ);
+				ctx->occ_cache[C] = occ;
+				}
+			occ = ctx->occ_cache[C];
 			if (occ <= 0)
 				return mb_fail(ctx, MB200_ECUDA, "k_posterior_sm (CM=%d) cannot be resident (smem %zu)", C, smem);
 			uint32_t nblocks = (uint32_t) occ*ctx->prop.multiProcessorCount;
@@ -428,17 +444,20 @@ static int run_posteriors(mb200_ctx *ctx, float *ea_out, const PostDebug *dbg, i
 			P.rows_stride = (size_t) lxmax*MB_CAP;
 			P.rowcnt_stride = ((size_t) lxmax + 31)/16*16;
 			size_t per_warp = P.fm_stride*4 + P.edge_stride*16 + P.rows_stride*8 + P.rowcnt_stride;
-			size_t free_b = 0, total_b = 0;
-			cudaMemGetInfo(&free_b, &total_b);
+			if (free_b == 0)
+				cudaMemGetInfo(&free_b, &total_b);
 			const size_t have = free_b + ctx->d_fm[C].cap + ctx->d_edge[C].cap + ctx->d_rows[C].cap + ctx->d_rowcnt[C].cap;
 			size_t use_warps = nwarps;
 			if (per_warp*use_warps > have*8/10)
 				use_warps = std::max<size_t>(MB_WARPS_PER_BLOCK, (have*8/10/per_warp)/MB_WARPS_PER_BLOCK*MB_WARPS_PER_BLOCK);
 			nblocks = (uint32_t)(use_warps/MB_WARPS_PER_BLOCK);
+			const size_t cap_before = ctx->d_fm[C].cap + ctx->d_edge[C].cap + ctx->d_rows[C].cap + ctx->d_rowcnt[C].cap;
 			ENSURE(ctx->d_fm[C], P.fm_stride*4*use_warps);
 			ENSURE(ctx->d_edge[C], P.edge_stride*16*use_warps);
 			ENSURE(ctx->d_rows[C], P.rows_stride*8*use_warps);
 			ENSURE(ctx->d_rowcnt[C], P.rowcnt_stride*use_warps);
+			if (ctx->d_fm[C].cap + ctx->d_edge[C].cap + ctx->d_rows[C].cap + ctx->d_rowcnt[C].cap != cap_before)
+				free_b = 0;                        // something was (re)allocated: ask again for the next size class
 			P.h = ctx->hmm;
 			P.matchT = (const float *) ctx->d_matchT.p;
 			P.insT = (const float *) ctx->d_insT.p;
@@ -449,7 +468,7 @@ static int run_posteriors(mb200_ctx *ctx, float *ea_out, const PostDebug *dbg, i
 			P.py = (const uint32_t *) ctx->d_py.p;
 			P.order = (const uint32_t *) ctx->d_order.p + bin_start[C];
 			P.nwork = (uint32_t) b.size();
-			P.counter = (uint32_t *) ctx->d_counters.p + C;
+			P.counter = (uint32_t *)((char *) ctx->d_cursor.p + 16) + C;
 			P.fm = (float *) ctx->d_fm[C].p;
 			P.edge = (float4 *) ctx->d_edge[C].p;
 			P.rows = (mb200_entry *) ctx->d_rows[C].p;
@@ -462,7 +481,7 @@ static int run_posteriors(mb200_ctx *ctx, float *ea_out, const PostDebug *dbg, i
 			P.entbase = (uint64_t *) ctx->d_entbase.p;
 			P.nnz = (uint32_t *) ctx->d_nnz.p;
 			P.ea = (float *) ctx->d_ea.p;
-			P.err = (int *) ctx->d_err.p;
+			P.err = (int *)((char *) ctx->d_cursor.p + 8);
 			if (dbg)
 				{
 				P.dbg_fwd = dbg->fwd; P.dbg_bwd = dbg->bwd; P.dbg_post = dbg->post; P.dbg_total = dbg->total;
@@ -478,12 +497,12 @@ static int run_posteriors(mb200_ctx *ctx, float *ea_out, const PostDebug *dbg, i
 			CU(cudaStreamWaitEvent(st, ctx->aux_done[k], 0));
 			}
 		CU(cudaEventRecord(ctx->ev2, st));
-		int err = 0;
-		unsigned long long used = 0;
-		CU(cudaMemcpyAsync(&err, ctx->d_err.p, sizeof(int), cudaMemcpyDeviceToHost, st));
-		CU(cudaMemcpyAsync(&used, ctx->d_cursor.p, sizeof(used), cudaMemcpyDeviceToHost, st));
+		CU(cudaMemcpyAsync(ctx->h_pinned, ctx->d_cursor.p, 16, cudaMemcpyDeviceToHost, st));
 		CU(cudaStreamSynchronize(st));
-		ctx->stats.d2h_bytes += sizeof(int) + sizeof(used);
+		unsigned long long used = 0;
+		memcpy(&used, ctx->h_pinned, sizeof used);
+		const int err = (int) ctx->h_pinned[2];
+		ctx->stats.d2h_bytes += 16;
 		ctx->store_nnz = used;
 		if (err == MB200_ENOMEM && used > est_entries)
 			{
@@ -495,8 +514,12 @@ static int run_posteriors(mb200_ctx *ctx, float *ea_out, const PostDebug *dbg, i
 			return mb_fail(ctx, MB200_EOVERFLOW, "a posterior row produced more than %d candidate entries", MB_CAP);
 		if (err != 0)
 			return mb_fail(ctx, err, "device error flag %d in k_posterior", err);
+		done = true;
 		break;
 		}
+	if (!done)
+		return mb_fail(ctx, MB200_ENOMEM, "posterior entry pool still too small after re-sizing (%llu entries)",
+		  (unsigned long long) est_entries);
 	if (ea_out)
 		{
 		CU(cudaMemcpyAsync(ea_out, ctx->d_ea.p, np*sizeof(float), cudaMemcpyDeviceToHost, st));

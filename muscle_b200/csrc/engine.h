@@ -51,10 +51,11 @@ struct mb200_ctx
 	std::vector<uint32_t> h_nnz;
 	std::vector<uint64_t> h_entbase;
 	bool h_index_valid = false;
-	DevBuf d_px, d_py, d_order, d_counters;
-	DevBuf d_rowoff, d_rowbase, d_entries, d_cursor, d_entbase, d_nnz, d_ea, d_err;
+	DevBuf d_px, d_py, d_order;
+	DevBuf d_rowoff, d_rowbase, d_entries, d_cursor, d_entbase, d_nnz, d_ea;     // d_cursor: control block, see prepare_plan
 	DevBuf d_entries2;                // second value buffer for the Jacobi update
 	DevBuf d_pack_off, d_pack_ent;    // packed image for exchange/export
+	uint64_t xchg_n_offsets = 0, xchg_n_entries = 0;      // sizes announced by mb200_store_exchange_begin
 	// transposed orientation of every pair (rows = positions of Y) for the relax kernel
 	DevBuf d_tr_rowoff, d_tr_rowbase, d_tr_entries, d_tr_entbase, d_tr_perm;
 	// column bit masks of every sparse row, both orientations (relax.cu): hdr = {first word slot,
@@ -64,6 +65,13 @@ struct mb200_ctx
 	DevBuf d_relax_order;
 	uint32_t relax_order_n = 0, relax_order_lo = 0, relax_order_hi = 0;
 	DevBuf d_tmp, d_tmp2;
+	// device-resident MSAs (align.cu): position -> column of every residue
+	// (same layout as d_codes) and, on the host, the column count of the MSA each sequence is in
+	DevBuf d_p2c, d_join;             // d_join: per-join scratch (maps, Post, traceback, path)
+	DevBuf d_stage;                   // BuildPost staging slots
+	std::vector<uint32_t> h_msa_cols;
+	bool msa_valid = false;
+	uint32_t *h_pinned = nullptr;     // 64 words of pinned host memory for small read-backs
 
 	// cached launch plan of the posterior stage (depends only on the pair list)
 	bool plan_valid = false, plan_is_allpairs = false;
@@ -79,6 +87,7 @@ struct mb200_ctx
 	cudaEvent_t aux_done[kStreams] = {};
 	DevBuf d_dbg;
 	int debug_force_c = 0;
+	int occ_cache[MB_MAX_C + 1] = {}, occ_cache_k = -1;     // resident CTAs/SM of k_posterior_sm per size class
 	};
 
 int mb_fail(mb200_ctx *ctx, int code, const char *fmt, ...);

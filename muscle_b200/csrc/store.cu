@@ -275,6 +275,108 @@ int mb200_export_all(mb200_ctx *ctx, uint32_t *offsets_concat, mb200_entry *entr
 	return MB200_OK;
 	}
 
+// In-place exchange (multi-GPU): the gathered image is received directly into library-owned
+// buffers, then adopted as the store -- no staging copy of a 10 GB image.
+int mb200_store_exchange_begin(mb200_ctx *ctx, uint64_t n_offsets, uint64_t n_entries, uint32_t **d_offsets,
+  mb200_entry **d_entries)
+	{
+	if (!ctx || !d_offsets || !d_entries || ctx->nseq < 2)
+		return mb_fail(ctx, MB200_EINVAL, "mb200_store_exchange_begin: bad argument");
+	cudaSetDevice(ctx->device);
+	uint64_t rows = 0;
+	for (uint32_t i = 0; i + 1 < ctx->nseq; ++i)
+		rows += (uint64_t)(ctx->h_len[i] + 1)*(ctx->nseq - 1 - i);
+	if (rows != n_offsets)
+		return mb_fail(ctx, MB200_EINVAL, "offset image has %llu slots, all pairs need %llu",
+		  (unsigned long long) n_offsets, (unsigned long long) rows);
+	// the caller's own packed store (d_rowoff / d_entries) stays valid and readable until commit
+	ENSURE(ctx->d_pack_off, n_offsets*sizeof(uint32_t));
+	ENSURE(ctx->d_pack_ent, (n_entries + 64)*sizeof(mb200_entry));
+	ctx->xchg_n_offsets = n_offsets;
+	ctx->xchg_n_entries = n_entries;
+	*d_offsets = (uint32_t *) ctx->d_pack_off.p;
+	*d_entries = (mb200_entry *) ctx->d_pack_ent.p;
+	return MB200_OK;
+	}
+
+// adopt d_pack_off / d_pack_ent (filled by the caller) as the store of all-pairs range [p_lo,p_hi)
+static int adopt_image(mb200_ctx *ctx, uint32_t p_lo, uint32_t p_hi, uint64_t n_offsets, uint64_t n_entries)
+	{
+	cudaStream_t st = ctx->stream;
+	const uint64_t all = (uint64_t) ctx->nseq*(ctx->nseq - 1)/2;
+	std::vector<uint32_t> px, py;
+	mb_allpairs_list(ctx->nseq, p_lo, p_hi, px, py);
+	const uint32_t np = (uint32_t) px.size();
+	std::vector<uint64_t> rowbase(np + 1, 0);
+	for (uint32_t k = 0; k < np; ++k)
+		rowbase[k + 1] = rowbase[k] + ctx->h_len[px[k]] + 1;
+	if (rowbase[np] != n_offsets)
+		return mb_fail(ctx, MB200_EINVAL, "offset image has %llu slots, pair range needs %llu",
+		  (unsigned long long) n_offsets, (unsigned long long) rowbase[np]);
+	ENSURE(ctx->d_px, np*sizeof(uint32_t));
+	ENSURE(ctx->d_py, np*sizeof(uint32_t));
+	ENSURE(ctx->d_rowbase, (np + 1)*sizeof(uint64_t));
+	ENSURE(ctx->d_entbase, (np + 1)*sizeof(uint64_t));
+	ENSURE(ctx->d_nnz, np*sizeof(uint32_t));
+	ENSURE(ctx->d_ea, np*sizeof(float));
+	ENSURE(ctx->d_tmp, (np + 1)*sizeof(uint64_t));
+	CU(cudaMemcpyAsync(ctx->d_px.p, px.data(), np*sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+	CU(cudaMemcpyAsync(ctx->d_py.p, py.data(), np*sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+	CU(cudaMemcpyAsync(ctx->d_rowbase.p, rowbase.data(), (np + 1)*sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+	k_nnz_from_rowoff<<<(np + 255)/256, 256, 0, st>>>(np, (const uint64_t *) ctx->d_rowbase.p,
+	  (const uint32_t *) ctx->d_pack_off.p, (uint32_t *) ctx->d_nnz.p, (uint64_t *) ctx->d_tmp.p);
+	CU(cudaGetLastError());
+	size_t tb = 0;
+	cub::DeviceScan::ExclusiveSum(nullptr, tb, (uint64_t *) ctx->d_tmp.p, (uint64_t *) ctx->d_entbase.p, (int) np, st);
+	ENSURE(ctx->d_tmp2, tb + 16);
+	cub::DeviceScan::ExclusiveSum(ctx->d_tmp2.p, tb, (uint64_t *) ctx->d_tmp.p, (uint64_t *) ctx->d_entbase.p, (int) np, st);
+	CU(cudaGetLastError());
+	ctx->stats.kernel_launches += 2;
+	std::vector<uint32_t> h_nnz(np);
+	std::vector<uint64_t> h_entbase(np);
+	CU(cudaMemcpyAsync(h_nnz.data(), ctx->d_nnz.p, np*sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+	CU(cudaMemcpyAsync(h_entbase.data(), ctx->d_entbase.p, np*sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+	CU(cudaStreamSynchronize(st));
+	uint64_t tot = 0;
+	for (uint32_t k = 0; k < np; ++k)
+		tot += h_nnz[k];
+	if (tot != n_entries)
+		return mb_fail(ctx, MB200_EINVAL, "entry image has %llu entries, offsets say %llu",
+		  (unsigned long long) n_entries, (unsigned long long) tot);
+	// everything validated: mutate the context
+	std::swap(ctx->d_rowoff, ctx->d_pack_off);
+	std::swap(ctx->d_entries, ctx->d_pack_ent);
+	ctx->h_px.swap(px);
+	ctx->h_py.swap(py);
+	ctx->h_rowbase.swap(rowbase);
+	ctx->h_nnz.swap(h_nnz);
+	ctx->h_entbase.swap(h_entbase);
+	ctx->plan_valid = false;
+	ctx->h_index_valid = true;
+	ctx->store_nnz = tot;
+	ctx->store_valid = true;
+	ctx->store_packed = true;
+	ctx->store_tr_valid = false;
+	ctx->store_masks_valid = false;
+	ctx->tr_values_stale = false;
+	ctx->store_allpairs = (p_lo == 0 && p_hi == all);
+	ctx->plan_is_allpairs = false;
+	ctx->store_p_lo = p_lo;
+	ctx->store_p_hi = p_hi;
+	return MB200_OK;
+	}
+
+int mb200_store_exchange_commit(mb200_ctx *ctx)
+	{
+	if (!ctx || ctx->xchg_n_offsets == 0)
+		return mb_fail(ctx, MB200_EINVAL, "mb200_store_exchange_commit: no exchange in progress");
+	cudaSetDevice(ctx->device);
+	const uint64_t all = (uint64_t) ctx->nseq*(ctx->nseq - 1)/2;
+	const int rc = adopt_image(ctx, 0, (uint32_t) all, ctx->xchg_n_offsets, ctx->xchg_n_entries);
+	ctx->xchg_n_offsets = ctx->xchg_n_entries = 0;
+	return rc;
+	}
+
 int mb200_store_load_allpairs(mb200_ctx *ctx, uint32_t p_lo, uint32_t p_hi, const uint32_t *d_offsets,
   uint64_t n_offsets, const mb200_entry *d_entries, uint64_t n_entries)
 	{
@@ -285,65 +387,34 @@ int mb200_store_load_allpairs(mb200_ctx *ctx, uint32_t p_lo, uint32_t p_hi, cons
 	const uint64_t all = (uint64_t) ctx->nseq*(ctx->nseq - 1)/2;
 	if (p_lo >= p_hi || p_hi > all)
 		return mb_fail(ctx, MB200_EINVAL, "pair range [%u,%u) invalid", p_lo, p_hi);
-	mb_allpairs_list(ctx->nseq, p_lo, p_hi, ctx->h_px, ctx->h_py);
-	const uint32_t np = (uint32_t) ctx->h_px.size();
-	std::vector<uint64_t> rowbase(np + 1, 0);
-	for (uint32_t k = 0; k < np; ++k)
-		rowbase[k + 1] = rowbase[k] + ctx->h_len[ctx->h_px[k]] + 1;
-	if (rowbase[np] != n_offsets)
-		return mb_fail(ctx, MB200_EINVAL, "offset image has %llu slots, pair range needs %llu",
-		  (unsigned long long) n_offsets, (unsigned long long) rowbase[np]);
-	ctx->h_rowbase = rowbase;
-	ctx->plan_valid = false;
-	ENSURE(ctx->d_px, np*sizeof(uint32_t));
-	ENSURE(ctx->d_py, np*sizeof(uint32_t));
-	ENSURE(ctx->d_rowbase, (np + 1)*sizeof(uint64_t));
-	ENSURE(ctx->d_entbase, (np + 1)*sizeof(uint64_t));
-	ENSURE(ctx->d_nnz, np*sizeof(uint32_t));
-	ENSURE(ctx->d_ea, np*sizeof(float));
-	ENSURE(ctx->d_tmp, (np + 1)*sizeof(uint64_t));
-	// the source image may alias our own buffers (single-rank round trip): stage before resizing
+	// the source image may alias our own buffers (single-rank round trip): stage before adopting
 	ENSURE(ctx->d_pack_off, n_offsets*sizeof(uint32_t));
 	ENSURE(ctx->d_pack_ent, (n_entries + 64)*sizeof(mb200_entry));
 	CU(cudaMemcpyAsync(ctx->d_pack_off.p, d_offsets, n_offsets*sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
 	if (n_entries)
 		CU(cudaMemcpyAsync(ctx->d_pack_ent.p, d_entries, n_entries*sizeof(mb200_entry), cudaMemcpyDeviceToDevice, st));
 	CU(cudaStreamSynchronize(st));
-	std::swap(ctx->d_rowoff, ctx->d_pack_off);
-	std::swap(ctx->d_entries, ctx->d_pack_ent);
-	CU(cudaMemcpyAsync(ctx->d_px.p, ctx->h_px.data(), np*sizeof(uint32_t), cudaMemcpyHostToDevice, st));
-	CU(cudaMemcpyAsync(ctx->d_py.p, ctx->h_py.data(), np*sizeof(uint32_t), cudaMemcpyHostToDevice, st));
-	CU(cudaMemcpyAsync(ctx->d_rowbase.p, rowbase.data(), (np + 1)*sizeof(uint64_t), cudaMemcpyHostToDevice, st));
-	k_nnz_from_rowoff<<<(np + 255)/256, 256, 0, st>>>(np, (const uint64_t *) ctx->d_rowbase.p,
-	  (const uint32_t *) ctx->d_rowoff.p, (uint32_t *) ctx->d_nnz.p, (uint64_t *) ctx->d_tmp.p);
-	CU(cudaGetLastError());
-	size_t tb = 0;
-	cub::DeviceScan::ExclusiveSum(nullptr, tb, (uint64_t *) ctx->d_tmp.p, (uint64_t *) ctx->d_entbase.p, (int) np, st);
-	ENSURE(ctx->d_tmp2, tb + 16);
-	cub::DeviceScan::ExclusiveSum(ctx->d_tmp2.p, tb, (uint64_t *) ctx->d_tmp.p, (uint64_t *) ctx->d_entbase.p, (int) np, st);
-	CU(cudaGetLastError());
-	ctx->stats.kernel_launches += 2;
-	ctx->h_nnz.resize(np);
-	ctx->h_entbase.resize(np);
-	CU(cudaMemcpyAsync(ctx->h_nnz.data(), ctx->d_nnz.p, np*sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-	CU(cudaMemcpyAsync(ctx->h_entbase.data(), ctx->d_entbase.p, np*sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
-	CU(cudaStreamSynchronize(st));
-	uint64_t tot = 0;
-	for (uint32_t k = 0; k < np; ++k)
-		tot += ctx->h_nnz[k];
-	if (tot != n_entries)
-		return mb_fail(ctx, MB200_EINVAL, "entry image has %llu entries, offsets say %llu",
-		  (unsigned long long) n_entries, (unsigned long long) tot);
-	ctx->h_index_valid = true;
-	ctx->store_nnz = tot;
-	ctx->store_valid = true;
-	ctx->store_packed = true;
-	ctx->store_tr_valid = false;
-	ctx->store_masks_valid = false;
-	ctx->store_allpairs = (p_lo == 0 && p_hi == all);
-	ctx->plan_is_allpairs = false;
-	ctx->store_p_lo = p_lo;
-	ctx->store_p_hi = p_hi;
+	return adopt_image(ctx, p_lo, p_hi, n_offsets, n_entries);
+	}
+
+int mb200_store_entries_ptr(mb200_ctx *ctx, mb200_entry **d_entries, uint64_t *n_entries)
+	{
+	if (!ctx || !d_entries)
+		return mb_fail(ctx, MB200_EINVAL, "mb200_store_entries_ptr: NULL argument");
+	const int rc = mb_store_pack_inplace(ctx);
+	if (rc != MB200_OK)
+		return rc;
+	*d_entries = (mb200_entry *) ctx->d_entries.p;
+	if (n_entries)
+		*n_entries = ctx->store_nnz;
+	return MB200_OK;
+	}
+
+int mb200_store_values_changed(mb200_ctx *ctx)
+	{
+	if (!ctx || !ctx->store_valid)
+		return mb_fail(ctx, MB200_EINVAL, "mb200_store_values_changed: no store");
+	ctx->tr_values_stale = true;
 	return MB200_OK;
 	}
 

@@ -67,33 +67,81 @@ def device_view(ptr, nbytes, device):
 	return torch.as_tensor(_DevView(ptr, nbytes), device=device)
 
 
-def gather_store(engine, group=None):
+def allgather_v_inplace(buf, bounds, group=None):
+	"""In-place all-gather-v: `buf` is the full-size destination on every rank, rank r's part
+	buf[bounds[r]:bounds[r+1]] is already in place; afterwards every rank holds every part.  One
+	broadcast per source rank, all in flight together (NCCL: ncclBroadcast straight into the final
+	position, no padding and no staging copy); empty parts are skipped on every rank alike."""
+	world = dist.get_world_size(group)
+	works = []
+	for r in range(world):
+		lo, hi = int(bounds[r]), int(bounds[r + 1])
+		if hi > lo:
+			works.append(dist.broadcast(buf[lo:hi], src=dist.get_global_rank(group, r) if group is not None else r,
+			  group=group, async_op=True))
+	for w in works:
+		w.wait()
+
+
+def _sizes(n, device, group):
+	t = torch.tensor([int(n)], dtype=torch.int64, device=device)
+	out = [torch.zeros_like(t) for _ in range(dist.get_world_size(group))]
+	dist.all_gather(out, t, group=group)
+	return [int(x.item()) for x in out]
+
+
+def gather_store(engine, group=None, have_store=True):
 	"""Exchange step 1: every rank contributes the packed image of its pair range; afterwards every
-	rank's engine holds the full all-pairs store.  Returns bytes received per rank."""
+	rank's engine holds the full all-pairs store.  The images are received directly into the
+	library's final buffers (mb200_store_exchange_begin/_commit).  A rank whose range is empty
+	(have_store False) contributes nothing.  Returns (bytes received per rank, device seconds)."""
 	dev = torch.device("cuda", torch.cuda.current_device())
-	po, no, pe, ne = engine.store_pack_ptrs()
-	offs = device_view(po, no*4, dev).view(torch.int32)
-	ents = device_view(pe, ne*8, dev).view(torch.int64)
-	all_offs, _ = allgather_v(offs, group)
-	all_ents, _ = allgather_v(ents, group)
-	n = engine.nseq
+	rank = dist.get_rank(group)
+	world = dist.get_world_size(group)
+	if have_store:
+		po, no, pe, ne = engine.store_pack_ptrs()
+	else:
+		po = pe = 0
+		no = ne = 0
+	n_off = _sizes(no, dev, group)
+	n_ent = _sizes(ne, dev, group)
+	ob = np.concatenate([[0], np.cumsum(n_off)]).astype(np.int64)
+	eb = np.concatenate([[0], np.cumsum(n_ent)]).astype(np.int64)
+	do, de = engine.store_exchange_begin(int(ob[-1]), int(eb[-1]))
+	all_offs = device_view(do, int(ob[-1])*4, dev).view(torch.int32)
+	all_ents = device_view(de, int(eb[-1])*8, dev).view(torch.int64)
+	# own part into place (device-to-device, on torch's stream like the collectives)
+	if no:
+		all_offs[int(ob[rank]):int(ob[rank + 1])].copy_(device_view(po, no*4, dev).view(torch.int32))
+	if ne:
+		all_ents[int(eb[rank]):int(eb[rank + 1])].copy_(device_view(pe, ne*8, dev).view(torch.int64))
+	ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+	ev0.record()
+	allgather_v_inplace(all_offs, ob, group)
+	allgather_v_inplace(all_ents, eb, group)
+	ev1.record()
 	# the library reads these buffers on its own (non-blocking) stream: finish the collective first
 	torch.cuda.current_stream().synchronize()
-	engine.store_load_allpairs(0, n*(n - 1)//2, all_offs.data_ptr(), all_offs.numel(), all_ents.data_ptr(), all_ents.numel())
-	return all_offs.numel()*4 + all_ents.numel()*8
+	engine.store_exchange_commit()
+	return int(ob[-1])*4 + int(eb[-1])*8, ev0.elapsed_time(ev1)*1e-3
 
 
 def gather_values(engine, entry_ranges, rank, group=None):
 	"""Exchange step 2: after a sharded consistency iteration each rank owns new values for the
-	entries of its pair range [entry_ranges[rank]); all-gather them and install the peers' parts."""
-	v = engine.store_values_torch()
-	lo, hi = entry_ranges[rank]
-	mine = v[lo:hi].contiguous()
-	allv, sizes = allgather_v(mine, group)
-	assert allv.numel() == v.numel(), (allv.numel(), v.numel())
+	entries of its pair range [entry_ranges[rank]); all-gather the entry ranges in place inside the
+	library's packed store.  Returns (bytes, device seconds)."""
+	dev = torch.device("cuda", torch.cuda.current_device())
+	pe, ne = engine.store_entries_ptr()
+	ents = device_view(pe, ne*8, dev).view(torch.int64)
+	bounds = [entry_ranges[0][0]] + [hi for (_, hi) in entry_ranges]
+	assert bounds[0] == 0 and bounds[-1] == ne, (bounds[0], bounds[-1], ne)
+	ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+	ev0.record()
+	allgather_v_inplace(ents, bounds, group)
+	ev1.record()
 	torch.cuda.current_stream().synchronize()        # see gather_store
-	engine.store_set_values_torch(allv, 0)
-	return allv.numel()*4
+	engine.store_values_changed()
+	return ne*8, ev0.elapsed_time(ev1)*1e-3
 
 
 def gather_ea(ea_local, ranges, n, group=None, distributed=None):

@@ -19,6 +19,10 @@ EXPORTS = [
 	"mb200_store_values", "mb200_store_set_values", "mb200_consistency_iter", "mb200_align_pairs",
 	"mb200_align_groups", "mb200_calc_post_dense", "mb200_get_stats", "mb200_residue_classes",
 	"mb200_debug_force_c", "mb200_set_nnz_per_row_cap",
+	"mb200_store_exchange_begin", "mb200_store_exchange_commit", "mb200_store_entries_ptr", "mb200_store_values_changed",
+	"mb200_group_create", "mb200_group_destroy", "mb200_group_last_error", "mb200_group_size", "mb200_group_ctx",
+	"mb200_group_set_hmm", "mb200_group_set_seqs", "mb200_group_posteriors_allpairs", "mb200_group_consistency_iter",
+	"mb200_group_get_stats",
 ]
 
 
@@ -31,6 +35,12 @@ class MB200Error(RuntimeError):
 class Stats(C.Structure):
 	_fields_ = [("kernel_launches", C.c_uint64), ("cells", C.c_uint64), ("last_kernel_ms", C.c_float),
 	  ("last_total_ms", C.c_float), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64)]
+
+
+class GroupStats(C.Structure):
+	_fields_ = [("ndev", C.c_uint32), ("cells", C.c_uint64), ("posterior_ms", C.c_float), ("exchange1_ms", C.c_float),
+	  ("exchange1_bytes_per_dev", C.c_uint64), ("relax_ms", C.c_float), ("relax_kernel_ms", C.c_float),
+	  ("exchange2_ms", C.c_float), ("exchange2_bytes_per_dev", C.c_uint64)]
 
 
 _lib = None
@@ -50,6 +60,13 @@ def load_library():
 		L.mb200_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
 		L.mb200_destroy.argtypes = [C.c_void_p]
 		L.mb200_destroy.restype = None
+		L.mb200_group_last_error.restype = C.c_char_p
+		L.mb200_group_last_error.argtypes = [C.c_void_p]
+		L.mb200_group_ctx.restype = C.c_void_p
+		L.mb200_group_ctx.argtypes = [C.c_void_p, C.c_int]
+		L.mb200_group_destroy.argtypes = [C.c_void_p]
+		L.mb200_group_destroy.restype = None
+		L.mb200_group_size.argtypes = [C.c_void_p]
 		_lib = L
 	return _lib
 
@@ -61,19 +78,24 @@ def _ptr(a):
 class Engine:
 	"""One context on one CUDA device (mb200_create .. mb200_destroy)."""
 
-	def __init__(self, device=0):
+	def __init__(self, device=0, _borrowed=None):
 		self.lib = load_library()
-		h = C.c_void_p()
-		rc = self.lib.mb200_create(int(device), C.byref(h))
-		if rc != 0:
-			raise MB200Error(rc, self.lib.mb200_last_error(None).decode())
-		self.h = h
+		self._owned = _borrowed is None
+		if _borrowed is not None:
+			self.h = C.c_void_p(_borrowed)       # a context owned by a Group
+		else:
+			h = C.c_void_p()
+			rc = self.lib.mb200_create(int(device), C.byref(h))
+			if rc != 0:
+				raise MB200Error(rc, self.lib.mb200_last_error(None).decode())
+			self.h = h
 		self.lens = None
 		self.nseq = 0
 
 	def close(self):
 		if getattr(self, "h", None):
-			self.lib.mb200_destroy(self.h)
+			if self._owned:
+				self.lib.mb200_destroy(self.h)
 			self.h = None
 
 	def __del__(self):
@@ -205,6 +227,29 @@ class Engine:
 		px, py = np.triu_indices(n, 1)
 		self._pairs = (px[p_lo:p_hi].astype(np.uint32), py[p_lo:p_hi].astype(np.uint32))
 
+	# ---- in-place exchange (multi-GPU)
+	def store_exchange_begin(self, n_offsets, n_entries):
+		"""-> (device ptr of the offsets image, device ptr of the entries image), library-owned"""
+		po, pe = C.c_void_p(), C.c_void_p()
+		self._ck(self.lib.mb200_store_exchange_begin(self.h, C.c_uint64(int(n_offsets)), C.c_uint64(int(n_entries)),
+		  C.byref(po), C.byref(pe)))
+		return po.value, pe.value
+
+	def store_exchange_commit(self):
+		self._ck(self.lib.mb200_store_exchange_commit(self.h))
+		n = self.nseq
+		px, py = np.triu_indices(n, 1)
+		self._pairs = (px.astype(np.uint32), py.astype(np.uint32))
+
+	def store_entries_ptr(self):
+		pe = C.c_void_p()
+		ne = C.c_uint64()
+		self._ck(self.lib.mb200_store_entries_ptr(self.h, C.byref(pe), C.byref(ne)))
+		return pe.value, ne.value
+
+	def store_values_changed(self):
+		self._ck(self.lib.mb200_store_values_changed(self.h))
+
 	# ---- posterior decoding
 	def align_pairs(self, store_pairs):
 		sp = np.ascontiguousarray(store_pairs, np.uint32)
@@ -236,3 +281,77 @@ class Engine:
 		s = Stats()
 		self._ck(self.lib.mb200_get_stats(self.h, C.byref(s)))
 		return {f: getattr(s, f) for f, _ in Stats._fields_}
+
+
+class Group:
+	"""Several GPUs driven by one process (mb200_group_*): what `muscle_b200 -align` uses."""
+
+	def __init__(self, devices=None):
+		self.lib = load_library()
+		g = C.c_void_p()
+		if devices is None:
+			rc = self.lib.mb200_group_create(0, None, C.byref(g))
+		else:
+			arr = (C.c_int*len(devices))(*devices)
+			rc = self.lib.mb200_group_create(len(devices), arr, C.byref(g))
+		if rc != 0:
+			raise MB200Error(rc, self.lib.mb200_group_last_error(None).decode())
+		self.g = g
+		self.size = int(self.lib.mb200_group_size(g))
+		self.nseq = 0
+		self.lens = None
+
+	def close(self):
+		if getattr(self, "g", None):
+			self.lib.mb200_group_destroy(self.g)
+			self.g = None
+
+	def __del__(self):
+		try:
+			self.close()
+		except Exception:
+			pass
+
+	def _ck(self, rc):
+		if rc != 0:
+			raise MB200Error(rc, self.lib.mb200_group_last_error(self.g).decode())
+
+	def engine(self, rank=0):
+		"""Engine view of one member context (borrowed; rank 0 runs the serial stages)"""
+		e = Engine(_borrowed=self.lib.mb200_group_ctx(self.g, int(rank)))
+		e.lens, e.nseq = self.lens, self.nseq
+		n = self.nseq
+		px, py = np.triu_indices(n, 1)
+		e._pairs = (px.astype(np.uint32), py.astype(np.uint32))
+		return e
+
+	def set_hmm(self, tables):
+		s = np.ascontiguousarray(tables["start"], np.float32)
+		t = np.ascontiguousarray(tables["trans"], np.float32).reshape(-1)
+		i = np.ascontiguousarray(tables["ins"], np.float32)
+		m = np.ascontiguousarray(tables["match"], np.float32).reshape(-1)
+		self._ck(self.lib.mb200_group_set_hmm(self.g, _ptr(s), _ptr(t), _ptr(i), _ptr(m),
+		  C.c_float(float(np.float32(tables["min_sparse_score"])))))
+
+	def set_seqs(self, seqs):
+		bs = [s if isinstance(s, (bytes, bytearray)) else s.encode() for s in seqs]
+		self.lens = np.array([len(b) for b in bs], np.int64)
+		off = np.zeros(len(bs) + 1, np.uint64)
+		off[1:] = np.cumsum(self.lens)
+		buf = np.frombuffer(b"".join(bs), dtype=np.uint8)
+		self.nseq = len(bs)
+		self._ck(self.lib.mb200_group_set_seqs(self.g, C.c_uint32(len(bs)), _ptr(buf), _ptr(off)))
+
+	def posteriors_allpairs(self, want_ea=True):
+		n = self.nseq
+		ea = np.empty(n*(n - 1)//2, np.float32) if want_ea else None
+		self._ck(self.lib.mb200_group_posteriors_allpairs(self.g, _ptr(ea)))
+		return ea
+
+	def consistency_iter(self):
+		self._ck(self.lib.mb200_group_consistency_iter(self.g))
+
+	def stats(self):
+		s = GroupStats()
+		self._ck(self.lib.mb200_group_get_stats(self.g, C.byref(s)))
+		return {f: getattr(s, f) for f, _ in GroupStats._fields_}

@@ -27,6 +27,8 @@ class MPCFlat:
 		self.m_Pairs = []
 		self.m_DistMx = None
 		self._ranges = None
+		self._eranges = None
+		self.timings = {}
 		self._rank, self._world = 0, 1
 		try:
 			import torch.distributed as dist
@@ -69,10 +71,14 @@ class MPCFlat:
 		n = self.GetSeqCount()
 		lens = [len(s) for s in self.m_MyInputSeqs]
 		self._ranges, _, _ = mdist.shard_ranges(lens, self._world)
+		self._eranges = None
 		lo, hi = self._ranges[self._rank]
 		ea = self.engine.posteriors_allpairs(lo, hi) if hi > lo else np.zeros(0, np.float32)
+		self.timings["posterior_ms"] = self.engine.stats()["last_total_ms"] if hi > lo else 0.0
 		if self._world > 1:
-			mdist.gather_store(self.engine, self.group)
+			nbytes, secs = mdist.gather_store(self.engine, self.group, have_store=hi > lo)
+			self.timings["exchange1_bytes"] = nbytes
+			self.timings["exchange1_ms"] = secs*1e3
 		m = mdist.gather_ea(ea, self._ranges, n, self.group, distributed=self._world > 1)
 		iu = np.triu_indices(n, 1)
 		self.m_DistMx[iu] = m[iu]
@@ -89,11 +95,17 @@ class MPCFlat:
 		from . import dist as mdist
 		lo, hi = self._ranges[self._rank] if self._ranges else (0, len(self.m_Pairs))
 		self.engine.consistency_iter(lo, hi)
+		st = self.engine.stats()
+		self.timings["relax_ms"] = st["last_total_ms"]
+		self.timings["relax_kernel_ms"] = st["last_kernel_ms"]
 		if self._world > 1:
-			nnz, _ = self.engine.store_nnz()
-			base = np.concatenate([[0], np.cumsum(nnz.astype(np.int64))])
-			eranges = [(int(base[a]), int(base[b])) for (a, b) in self._ranges]
-			mdist.gather_values(self.engine, eranges, self._rank, self.group)
+			if self._eranges is None:
+				nnz, _ = self.engine.store_nnz()
+				base = np.concatenate([[0], np.cumsum(nnz.astype(np.int64))])
+				self._eranges = [(int(base[a]), int(base[b])) for (a, b) in self._ranges]
+			nbytes, secs = mdist.gather_values(self.engine, self._eranges, self._rank, self.group)
+			self.timings["exchange2_bytes"] = nbytes
+			self.timings["exchange2_ms"] = secs*1e3
 
 	def GetSparsePost(self, pair_index):
 		"""(offsets[LX+1], entries[nnz]) in MySparseMx layout (mpcflat.cpp:88-98)"""

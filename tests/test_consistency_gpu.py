@@ -1,7 +1,7 @@
-"""GPU parity of the consistency (relax) iteration, the packed store and the posterior decoding
-kernels against the CPU oracle.  The relax arithmetic is fp32 mul/add in the reference's order, so
-given IDENTICAL inputs the update is compared bit-exact; inputs come from the GPU posterior stage
-(expf differs from glibc by <= 2 ulp), therefore the oracle is fed the GPU store itself."""
+"""GPU parity of the consistency (relax) iteration, the packed store, the multi-device exchange
+and the posterior decoding kernels against the CPU oracle and the compiled reference's goldens.
+The relax arithmetic is fp32 mul/add in the reference's order and the posterior stage is itself
+bit-exact (glibc-exact expf on the device), so everything here is compared with tolerance 0."""
 import os
 import numpy as np
 import pytest
@@ -165,22 +165,79 @@ def test_virtual_ranks_pipeline(tables, oracle, world):
 		img_ent.append(mdist.device_view(pe, ne*8, dev).view(torch.int64).clone())
 	assert np.array_equal(np.concatenate(eas), ea_s)
 	all_off, all_ent = torch.cat(img_off), torch.cat(img_ent)
-	for e in engines:
-		e.store_load_allpairs(0, npairs, all_off.data_ptr(), all_off.numel(), all_ent.data_ptr(), all_ent.numel())
+	# even ranks: copying load (mb200_store_load_allpairs); odd ranks: in-place exchange buffers
+	# (mb200_store_exchange_begin/_commit), filled here by a device copy as the collective would
+	for r, e in enumerate(engines):
+		if r % 2 == 0:
+			e.store_load_allpairs(0, npairs, all_off.data_ptr(), all_off.numel(), all_ent.data_ptr(), all_ent.numel())
+		else:
+			do, de = e.store_exchange_begin(all_off.numel(), all_ent.numel())
+			mdist.device_view(do, all_off.numel()*4, dev).view(torch.int32).copy_(all_off)
+			mdist.device_view(de, all_ent.numel()*8, dev).view(torch.int64).copy_(all_ent)
+			torch.cuda.synchronize()
+			e.store_exchange_commit()
 	nnz, _ = engines[0].store_nnz()
 	base = np.concatenate([[0], np.cumsum(nnz.astype(np.int64))])
 	for it in range(2):
 		parts = []
 		for r, (lo, hi) in enumerate(ranges):
 			engines[r].consistency_iter(lo, hi)
-			v = engines[r].store_values_torch()
+			pe, ne = engines[r].store_entries_ptr()
+			v = mdist.device_view(pe, ne*8, dev).view(torch.int64)
 			parts.append(v[int(base[lo]):int(base[hi])].clone())
 		allv = torch.cat(parts)
 		for e in engines:
-			e.store_set_values_torch(allv, 0)
+			pe, ne = e.store_entries_ptr()
+			mdist.device_view(pe, ne*8, dev).view(torch.int64).copy_(allv)
+			torch.cuda.synchronize()
+			e.store_values_changed()
 	for r, e in enumerate(engines):
 		offs, ents = e.export_all()
 		for p in range(npairs):
 			assert np.array_equal(offs[p], offs_s[p]) and ents[p].tobytes() == ents_s[p].tobytes(), (r, p)
 		e.close()
 	single.close()
+
+
+def test_group_one_device_equals_engine(tables):
+	"""the single-process multi-device front end with one member must equal a plain engine"""
+	from muscle_b200.engine import Engine, Group
+	seqs = synth.make_family(12, 80, 20, seed=33)
+	e = Engine(0); e.set_hmm(tables); e.set_seqs(seqs)
+	ea = e.posteriors_allpairs()
+	e.consistency_iter(); e.consistency_iter()
+	offs, ents = e.export_all()
+	g = Group([0]); g.set_hmm(tables); g.set_seqs(seqs)
+	ea_g = g.posteriors_allpairs()
+	g.consistency_iter(); g.consistency_iter()
+	offs_g, ents_g = g.engine(0).export_all()
+	assert np.array_equal(ea, ea_g)
+	for p in range(len(offs)):
+		assert np.array_equal(offs[p], offs_g[p]) and ents[p].tobytes() == ents_g[p].tobytes(), p
+	assert g.stats()["ndev"] == 1 and g.stats()["relax_kernel_ms"] > 0
+	g.close(); e.close()
+
+
+def test_group_all_devices_equal_engine(tables):
+	""">= 2 GPUs: sharded posteriors + peer-memory all-gather-v + sharded relax + entry exchange
+	must leave EVERY device bit-identical to a single-device run"""
+	import torch
+	if torch.cuda.device_count() < 2:
+		pytest.skip("needs 2 GPUs")
+	from muscle_b200.engine import Engine, Group
+	seqs = synth.make_family(30, 100, 25, seed=35)
+	e = Engine(0); e.set_hmm(tables); e.set_seqs(seqs)
+	ea = e.posteriors_allpairs()
+	e.consistency_iter(); e.consistency_iter()
+	offs, ents = e.export_all()
+	g = Group(None); g.set_hmm(tables); g.set_seqs(seqs)
+	ea_g = g.posteriors_allpairs()
+	g.consistency_iter(); g.consistency_iter()
+	assert np.array_equal(ea, ea_g)
+	st = g.stats()
+	assert st["ndev"] == torch.cuda.device_count() and st["exchange1_bytes_per_dev"] > 0 and st["exchange2_bytes_per_dev"] > 0
+	for r in range(g.size):
+		offs_g, ents_g = g.engine(r).export_all()
+		for p in range(len(offs)):
+			assert np.array_equal(offs[p], offs_g[p]) and ents[p].tobytes() == ents_g[p].tobytes(), (r, p)
+	g.close(); e.close()

@@ -52,6 +52,19 @@ def _worker(rank, world, port, q):
 	# empty shard on one rank
 	e, sz = mdist.allgather_v(torch.zeros(0 if rank == 0 else 5, dtype=torch.float32))
 	ok = ok and e.numel() == 5 and sz == [0, 5]
+	# in-place all-gather-v (what the store / entry-range exchanges use): own part in place, then
+	# one broadcast per source rank; an empty part in the middle must not hang anybody
+	bounds = [0, 137, 137 if False else 1000]
+	buf = torch.zeros(1000, dtype=torch.int64)
+	buf[bounds[rank]:bounds[rank + 1]] = full[bounds[rank]:bounds[rank + 1]]
+	mdist.allgather_v_inplace(buf, bounds)
+	ok = ok and bool((buf == full).all())
+	b2 = [0, 0, 10] if rank >= 0 else None          # rank 0 owns nothing
+	buf2 = torch.zeros(10, dtype=torch.float32)
+	if rank == 1:
+		buf2[:] = 7.0
+	mdist.allgather_v_inplace(buf2, b2)
+	ok = ok and bool((buf2 == 7.0).all())
 	q.put((rank, ok))
 	dist.destroy_process_group()
 
