@@ -135,8 +135,8 @@ int mb200_consistency_iter(mb200_ctx *ctx, uint32_t p_lo, uint32_t p_hi);
 /* Batched CalcAlnFlat (calcalnflat.cpp:6-46) + TraceBackFlat (tracebackflat.cpp:3-37) on the
  * stored pairs: for each listed store pair, densify its sparse posterior, run the max-sum DP with
  * Best3 tie order (best3.h:5-28) and trace back.  paths_out: concatenated, pair k's path starts
- * at path_off[k] (path_off[k] = sum_{m<k}(LX_m+LY_m+1)), NUL terminated, letters B/X/Y;
- * scores_out[k] = DP score.  Serves AlignPairFlat (alignpairflat.cpp:23) and
+ * at path_off[k] and owns path_off[k+1]-path_off[k] >= LX_k+LY_k+1 bytes (path_off has n+1 entries,
+ * path_off[n] = size of paths_out), NUL terminated, letters B/X/Y; scores_out[k] = DP score.  Serves AlignPairFlat (alignpairflat.cpp:23) and
  * PProg::GetPostPairsAlignedFlat (getpostpairsalignedflat.cpp:62-90). */
 int mb200_align_pairs(mb200_ctx *ctx, uint32_t n, const uint32_t *store_pairs,
                       char *paths_out, const uint64_t *path_off, float *scores_out);
@@ -151,6 +151,28 @@ int mb200_align_groups(mb200_ctx *ctx,
                        uint32_t na, const uint32_t *ids_a, const uint32_t *pos2col_a, uint32_t cols_a,
                        uint32_t nb, const uint32_t *ids_b, const uint32_t *pos2col_b, uint32_t cols_b,
                        char *path_out, float *score_out, float *post_out);
+
+/* ---- device-resident multiple alignments --------------------------- */
+/* The data path of MPCFlat::ProgressiveAlign / ProgAln (progalnflat.cpp:41-100) and MPCFlat::RefineIter
+ * (refineflat.cpp:4-31) without per-join host<->device traffic of column maps: the library keeps, for
+ * every sequence, the position -> column map of the MSA it currently belongs to
+ * (Sequence::GetPosToCol, sequence.cpp:144-154).
+ *   mb200_msa_reset   every sequence becomes a one-row MSA (the leaves, progalnflat.cpp:79-85).
+ *   mb200_msa_join    A and B are disjoint lists of sequence ids in MSA row order; all members of A
+ *                     (resp. B) must currently share one MSA, of which A may be a subset.  Does, on
+ *                     the device: MultiSequence::Project of each group (project.cpp:16-69: all-gap
+ *                     columns dropped -- a no-op when the group is a whole MSA), MPCFlat::BuildPost
+ *                     (buildpostflat.cpp:18-105), CalcAlnFlat + traceback (calcalnflat.cpp:6-46),
+ *                     and Sequence::AddGapsPath (sequence.cpp:115-140) applied to the column maps of
+ *                     every member ('X' for A, 'Y' for B, alnalnsflat.cpp:36-50).  Afterwards all
+ *                     members share one MSA of *cols_out columns whose row order is A then B.
+ *                     path_out (may be NULL; path_cap bytes >= cols_a+cols_b+1) receives the path.
+ *   mb200_msa_export  concatenated position -> column maps of the listed sequences (what the host
+ *                     needs to print the final MSA); cols_out[k] (may be NULL) = columns of its MSA. */
+int mb200_msa_reset(mb200_ctx *ctx);
+int mb200_msa_join(mb200_ctx *ctx, uint32_t na, const uint32_t *ids_a, uint32_t nb, const uint32_t *ids_b,
+                   uint32_t *cols_out, float *score_out, char *path_out, uint32_t path_cap);
+int mb200_msa_export(mb200_ctx *ctx, uint32_t n, const uint32_t *ids, uint32_t *pos2col_out, uint32_t *cols_out);
 
 /* ---- per-pair debug/parity surface -------------------------------------------------------- */
 /* CalcPost (calcpost.cpp:4-36) for one pair with the dense result copied to the host:

@@ -1,33 +1,50 @@
 // integration/mpcflat_b200_shim.cpp -- the reference-side binding a MUSCLE maintainer would add to
-// make libmuscle_b200.so the pair engine of `muscle -align` / `-super5`.
+// make libmuscle_b200.so the pair engine of `muscle -align`.
 //
 // It is compiled against the UNMODIFIED reference headers and replaces, at link time, exactly the
-// three MPCFlat members that own the hot loops:
-//   MPCFlat::CalcPosteriors   (mpcflat.cpp:214-252)  -> mb200_posteriors_allpairs
-//   MPCFlat::ConsIter         (consflat.cpp:5-23)    -> mb200_consistency_iter
-//   MPCFlat::AlignAlns        (alnalnsflat.cpp:7-52) -> mb200_align_groups (+ the reference's own gap insertion)
-// Everything else (FASTA I/O, dereplication, UPGMA guide tree, join order, progressive alignment
-// and refinement control flow, MSA output) is the reference's own code, untouched.
-// Errors keep the reference convention: Die() -> message + exit(1) (myutils.cpp:883).
+// MPCFlat members that own the hot loops and the data path of the join/refine loop:
+//   MPCFlat::CalcPosteriors   (mpcflat.cpp:214-252)    -> mb200_group_posteriors_allpairs (all visible GPUs)
+//   MPCFlat::CalcPosterior    (calcposteriorflat.cpp:45-92, per-pair form used by -profalign/-profseq)
+//                                                      -> deferred; the batch runs before the first AlignAlns
+//   MPCFlat::ConsIter         (consflat.cpp:5-23)      -> mb200_group_consistency_iter
+//   MPCFlat::AlignAlns        (alnalnsflat.cpp:7-52)   -> mb200_align_groups (+ the reference's own gap insertion)
+//   MPCFlat::ProgressiveAlign (progalnflat.cpp:73-100) -> mb200_msa_reset + one mb200_msa_join per guide-tree join
+//   MPCFlat::Refine           (mpcflat.cpp:255-265) / RefineIter (refineflat.cpp:4-31)
+//                                                      -> one mb200_msa_join per bipartition (same rand() stream)
+// Everything else (FASTA I/O, dereplication, UPGMA guide tree, join order, sorting, MSA output) is the
+// reference's own code, untouched.  Errors keep the reference convention: Die() -> message +
+// exit(1) (myutils.cpp:883).  There is no CPU fallback: inputs the engine does not implement (Mega
+// feature profiles) stop with a message instead of silently running something else.
 #include "muscle.h"
 #include "mpcflat.h"
 #include "pairhmm.h"
+#include "mega.h"
 #include "../include/muscle_b200.h"
 
 #include <chrono>
-static mb200_ctx *g_Ctx = 0;
+static mb200_group *g_Group = 0;
+static mb200_ctx *g_Ctx = 0;                       // device 0 of the group: the serial stages
+static const MPCFlat *g_StoreOwner = 0;            // whose posteriors the device store holds
+static const MPCFlat *volatile g_Deferred = 0;     // CalcPosterior() was called on this object: batch pending
+static vector<uint> g_MSAOrder;                    // input-sequence index of every row of m_MSA
 
 // MB200_TRACE=1: wall-time split of the replaced members, printed at exit
-static double g_TPrep = 0, g_TLib = 0, g_TGaps = 0, g_TPost = 0, g_TCons = 0;
-static uint g_NAlign = 0;
+static double g_TPost = 0, g_TCons = 0, g_TProg = 0, g_TRefine = 0, g_TAlign = 0;
+static uint g_NAlign = 0, g_NJoin = 0;
 static double Now()
 	{
 	return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
 	}
 static void TraceReport()
 	{
-	fprintf(stderr, "\n[mb200 trace] CalcPosteriors %.2f s, ConsIter %.2f s, AlignAlns x%u: prepare %.2f s, "
-	  "mb200_align_groups %.2f s, AddGapsPath %.2f s\n", g_TPost, g_TCons, g_NAlign, g_TPrep, g_TLib, g_TGaps);
+	mb200_group_stats S;
+	memset(&S, 0, sizeof S);
+	if (g_Group != 0)
+		mb200_group_get_stats(g_Group, &S);
+	fprintf(stderr, "\n[mb200 trace] %u GPU(s): CalcPosteriors %.2f s (store exchange %.1f ms, %.2f GB/GPU), ConsIter %.2f s "
+	  "(last: kernel %.1f ms, exchange %.1f ms), ProgressiveAlign %.2f s, Refine %.2f s (%u device joins), AlignAlns x%u %.2f s\n",
+	  S.ndev, g_TPost, S.exchange1_ms, S.exchange1_bytes_per_dev/1e9, g_TCons, S.relax_kernel_ms, S.exchange2_ms,
+	  g_TProg, g_TRefine, g_NJoin, g_NAlign, g_TAlign);
 	}
 
 static void Check(int rc, const char *What)
@@ -36,63 +53,103 @@ static void Check(int rc, const char *What)
 		Die("libmuscle_b200 %s failed (%d): %s", What, rc, mb200_last_error(g_Ctx));
 	}
 
-static void EnsureCtx()
+static void CheckG(int rc, const char *What)
 	{
-	if (g_Ctx != 0)
-		return;
-	int Device = 0;
-	const char *s = getenv("MB200_DEVICE");
-	if (s != 0)
-		Device = atoi(s);
-	int rc = mb200_create(Device, &g_Ctx);
 	if (rc != MB200_OK)
-		Die("libmuscle_b200 mb200_create failed (%d): %s", rc, mb200_last_error(0));
+		Die("libmuscle_b200 %s failed (%d): %s", What, rc, mb200_group_last_error(g_Group));
+	}
+
+static void NoMega()
+	{
+	if (Mega::m_Loaded)
+		Die("muscle_b200: Mega feature profiles (-mega / .mega input) are not implemented by the B200 engine; "
+		  "use the CPU build of muscle for this input");
+	}
+
+static void EnsureGroup()
+	{
+	if (g_Group != 0)
+		return;
+	// MB200_DEVICES=n: use the first n visible GPUs (default: all); MB200_DEVICE=d: only device d
+	int rc;
+	const char *one = getenv("MB200_DEVICE");
+	const char *cnt = getenv("MB200_DEVICES");
+	if (one != 0)
+		{
+		int Device = atoi(one);
+		rc = mb200_group_create(1, &Device, &g_Group);
+		}
+	else
+		rc = mb200_group_create(cnt != 0 ? atoi(cnt) : 0, 0, &g_Group);
+	if (rc != MB200_OK)
+		Die("libmuscle_b200 mb200_group_create failed (%d): %s", rc, mb200_group_last_error(0));
+	g_Ctx = mb200_group_ctx(g_Group, 0);
 	if (getenv("MB200_TRACE") != 0)
 		atexit(TraceReport);
 	}
 
-void MPCFlat::CalcPosteriors()
+// the whole posterior stage of one MPCFlat object on the device(s)
+static void RunPosteriors(MPCFlat &M)
 	{
-	const double T0 = Now();
-	EnsureCtx();
-	const uint SeqCount = GetSeqCount();
-	const uint PairCount = SIZE(m_Pairs);
+	NoMega();
+	EnsureGroup();
+	const uint SeqCount = M.GetSeqCount();
+	const uint PairCount = SIZE(M.m_Pairs);
 	asserta(PairCount > 0);
 
 // PairHMM tables are process-global statics rewritten between replicates (align.cpp:30-40):
 // upload them every time, exactly as the host computed them.
-	Check(mb200_set_hmm(g_Ctx, PairHMM::m_StartScore, &PairHMM::m_TransScore[0][0],
-	  PairHMM::m_InsScore, &PairHMM::m_MatchScore[0][0], MIN_SPARSE_SCORE), "mb200_set_hmm");
+	CheckG(mb200_group_set_hmm(g_Group, PairHMM::m_StartScore, &PairHMM::m_TransScore[0][0],
+	  PairHMM::m_InsScore, &PairHMM::m_MatchScore[0][0], MIN_SPARSE_SCORE), "mb200_group_set_hmm");
 
 	vector<byte> Bytes;
 	vector<uint64_t> Offsets;
 	Offsets.push_back(0);
 	for (uint i = 0; i < SeqCount; ++i)
 		{
-		const byte *Seq = GetBytePtr(i);
-		const uint L = GetSeqLength(i);
+		const byte *Seq = M.GetBytePtr(i);
+		const uint L = M.GetSeqLength(i);
 		Bytes.insert(Bytes.end(), Seq, Seq + L);
 		Offsets.push_back(Bytes.size());
 		}
-	Check(mb200_set_seqs(g_Ctx, SeqCount, Bytes.data(), Offsets.data()), "mb200_set_seqs");
+	CheckG(mb200_group_set_seqs(g_Group, SeqCount, Bytes.data(), Offsets.data()), "mb200_group_set_seqs");
 
-	ProgressStep(0, 2, "Calc posteriors (B200)");
 	vector<float> EAs(PairCount);
-	Check(mb200_posteriors_allpairs(g_Ctx, 0, PairCount, EAs.data()), "mb200_posteriors_allpairs");
+	CheckG(mb200_group_posteriors_allpairs(g_Group, EAs.data()), "mb200_group_posteriors_allpairs");
 	for (uint PairIndex = 0; PairIndex < PairCount; ++PairIndex)
 		{
-		const pair<uint, uint> &Pair = GetPair(PairIndex);
+		const pair<uint, uint> &Pair = M.GetPair(PairIndex);
 		const float EA = EAs[PairIndex];
-		m_DistMx[Pair.first][Pair.second] = EA;			// calcposteriorflat.cpp:89-91
-		m_DistMx[Pair.second][Pair.first] = EA;
+		M.m_DistMx[Pair.first][Pair.second] = EA;			// calcposteriorflat.cpp:89-91
+		M.m_DistMx[Pair.second][Pair.first] = EA;
 		}
+	g_StoreOwner = &M;
+	g_Deferred = 0;
+	}
+
+// a caller is about to read the store of this object: run the deferred batch if there is one
+static void NeedStore(MPCFlat &M)
+	{
+	if (g_Deferred == &M)
+		RunPosteriors(M);
+	if (g_StoreOwner != &M)
+		Die("muscle_b200: posteriors of this MPCFlat object are not on the device "
+		  "(AlignAlns / ProgressiveAlign called before CalcPosteriors)");
+	}
+
+void MPCFlat::CalcPosteriors()
+	{
+	const double T0 = Now();
+	ProgressStep(0, 2, "Calc posteriors (B200)");
+	RunPosteriors(*this);
 	ProgressStep(1, 2, "Calc posteriors (B200)");
 	g_TPost += Now() - T0;
 	// The sparse posteriors stay resident in HBM for ConsIter / AlignAlns (the store replaces
-	// m_SparsePosts1/2).  Set MB200_EXPORT_SPARSE=1 to also fill the host MySparseMx objects, e.g.
-	// for commands that read GetSparsePost() directly (-profalign).
+	// m_SparsePosts1/2).  Set MB200_EXPORT_SPARSE=1 to also fill the host MySparseMx objects for
+	// code that reads GetSparsePost() directly.
 	if (getenv("MB200_EXPORT_SPARSE") != 0)
 		{
+		const uint PairCount = SIZE(m_Pairs);
 		for (uint PairIndex = 0; PairIndex < PairCount; ++PairIndex)
 			{
 			const pair<uint, uint> &Pair = GetPair(PairIndex);
@@ -112,14 +169,23 @@ void MPCFlat::CalcPosteriors()
 		}
 	}
 
+// -profalign / -profseq call this once per cross pair from an OpenMP loop (profalign.cpp:36-49,
+// profseq.cpp:42) and then AlignAlns: the pairs are independent, so the work is deferred and done as
+// ONE all-pairs batch on the device when AlignAlns needs the store (a superset of the cross pairs).
+void MPCFlat::CalcPosterior(uint PairIndex)
+	{
+	(void) PairIndex;
+	g_Deferred = this;
+	}
+
 void MPCFlat::ConsIter(uint Iter)
 	{
-	EnsureCtx();
+	NeedStore(*this);
 	const uint PairCount = SIZE(m_Pairs);
 	asserta(PairCount > 0);
 	ProgressStep(0, 2, "Consistency (%u/%u) (B200)", Iter + 1, m_ConsistencyIterCount);
 	const double T0 = Now();
-	Check(mb200_consistency_iter(g_Ctx, 0, PairCount), "mb200_consistency_iter");
+	CheckG(mb200_group_consistency_iter(g_Group), "mb200_group_consistency_iter");
 	g_TCons += Now() - T0;
 	ProgressStep(1, 2, "Consistency (%u/%u) (B200)", Iter + 1, m_ConsistencyIterCount);
 	// the Jacobi buffer swap (consflat.cpp:22) happens inside the library
@@ -127,7 +193,7 @@ void MPCFlat::ConsIter(uint Iter)
 
 MultiSequence *MPCFlat::AlignAlns(const MultiSequence &MSA1, const MultiSequence &MSA2, float *ptrScore)
 	{
-	EnsureCtx();
+	NeedStore(*this);
 	const double T0 = Now();
 	++g_NAlign;
 	const uint SeqCount1 = MSA1.GetSeqCount();
@@ -153,12 +219,8 @@ MultiSequence *MPCFlat::AlignAlns(const MultiSequence &MSA1, const MultiSequence
 
 	vector<char> PathBuf(ColCount1 + ColCount2 + 1);
 	float Score = 0;
-	const double T1 = Now();
-	g_TPrep += T1 - T0;
 	Check(mb200_align_groups(g_Ctx, SeqCount1, Ids1.data(), P2C1.data(), ColCount1,
 	  SeqCount2, Ids2.data(), P2C2.data(), ColCount2, PathBuf.data(), &Score, 0), "mb200_align_groups");
-	const double T2 = Now();
-	g_TLib += T2 - T1;
 	if (ptrScore != 0)
 		*ptrScore = Score;
 	const string Path(PathBuf.data());
@@ -177,6 +239,107 @@ MultiSequence *MPCFlat::AlignAlns(const MultiSequence &MSA1, const MultiSequence
 		Sequence *AlignedRow = InputRow->AddGapsPath(Path, 'Y');
 		result->AddSequence(AlignedRow, true);
 		}
-	g_TGaps += Now() - T2;
+	g_TAlign += Now() - T0;
 	return result;
+	}
+
+// m_MSA from the device-resident column maps, rows in the given order of input-sequence indexes
+static MultiSequence *MSAFromDevice(const MPCFlat &M, const vector<uint> &Order)
+	{
+	const uint N = SIZE(Order);
+	uint64_t Total = 0;
+	for (uint k = 0; k < N; ++k)
+		Total += M.GetSeqLength(Order[k]);
+	vector<uint> Maps(Total), Cols(N);
+	Check(mb200_msa_export(g_Ctx, N, Order.data(), Maps.data(), Cols.data()), "mb200_msa_export");
+	MultiSequence *MS = new MultiSequence;
+	uint64_t Off = 0;
+	for (uint k = 0; k < N; ++k)
+		{
+		const uint s = Order[k];
+		const Sequence *In = M.m_MyInputSeqs->GetSequence(s);
+		const uint L = M.GetSeqLength(s);
+		asserta(Cols[k] == Cols[0]);
+		Sequence *Row = NewSequence();
+		Row->m_Label = In->m_Label;
+		Row->m_CharVec.assign(Cols[k], '-');
+		const byte *Letters = M.GetBytePtr(s);
+		for (uint i = 0; i < L; ++i)
+			Row->m_CharVec[Maps[Off + i]] = (char) Letters[i];
+		Off += L;
+		MS->AddSequence(Row, true);
+		}
+	return MS;
+	}
+
+// progalnflat.cpp:73-100 with ProgAln (:41-71) folded in: the N-1 joins of the guide tree run on the
+// device-resident column maps; the host only keeps which sequences a node holds, in MSA row order
+// (AlignAlns appends the rows of MSA2 to those of MSA1, alnalnsflat.cpp:36-50).
+void MPCFlat::ProgressiveAlign()
+	{
+	NeedStore(*this);
+	const double T0 = Now();
+	const uint SeqCount = m_MyInputSeqs->GetSeqCount();
+	const uint JoinCount = SeqCount - 1;
+	asserta(SIZE(m_JoinIndexes1) == JoinCount);
+	asserta(SIZE(m_JoinIndexes2) == JoinCount);
+	ValidateJoinOrder(m_JoinIndexes1, m_JoinIndexes2);
+
+	Check(mb200_msa_reset(g_Ctx), "mb200_msa_reset");
+	vector<vector<uint> > Members(SeqCount);
+	for (uint i = 0; i < SeqCount; ++i)
+		Members[i].push_back(i);
+	for (uint JoinIndex = 0; JoinIndex < JoinCount; ++JoinIndex)
+		{
+		const uint Index1 = m_JoinIndexes1[JoinIndex];
+		const uint Index2 = m_JoinIndexes2[JoinIndex];
+		asserta(Index1 < SIZE(Members) && Index2 < SIZE(Members));
+		vector<uint> &A = Members[Index1];
+		vector<uint> &B = Members[Index2];
+		asserta(!A.empty() && !B.empty());
+		Check(mb200_msa_join(g_Ctx, SIZE(A), A.data(), SIZE(B), B.data(), 0, 0, 0, 0), "mb200_msa_join");
+		++g_NJoin;
+		vector<uint> AB(A);
+		AB.insert(AB.end(), B.begin(), B.end());
+		A.clear();
+		B.clear();
+		Members.push_back(AB);
+		}
+	g_MSAOrder = Members.back();
+	asserta(SIZE(g_MSAOrder) == SeqCount);
+	m_MSA = MSAFromDevice(*this, g_MSAOrder);
+	g_TProg += Now() - T0;
+	}
+
+// mpcflat.cpp:255-265 + refineflat.cpp:4-31.  The bipartition consumes the libc rand() stream exactly
+// like the reference (one rand() per MSA row, in row order); MultiSequence::Project (all-gap columns
+// dropped) and AlignAlns happen on the device maps.
+void MPCFlat::Refine()
+	{
+	const uint SeqCount = GetSeqCount();
+	if (SeqCount < 3)
+		return;
+	NeedStore(*this);
+	asserta(m_MSA != 0);
+	asserta(SIZE(g_MSAOrder) == SeqCount && m_MSA->GetSeqCount() == SeqCount);
+	const double T0 = Now();
+	for (uint Iter = 0; Iter < m_RefineIterCount; ++Iter)
+		{
+		ProgressStep(Iter, m_RefineIterCount, "Refining (B200)");
+		vector<uint> A, B;
+		for (uint SeqIndex = 0; SeqIndex < SeqCount; SeqIndex++)
+			if (rand()%2 == 0)
+				A.push_back(g_MSAOrder[SeqIndex]);
+			else
+				B.push_back(g_MSAOrder[SeqIndex]);
+		if (A.empty() || B.empty())
+			continue;
+		Check(mb200_msa_join(g_Ctx, SIZE(A), A.data(), SIZE(B), B.data(), 0, 0, 0, 0), "mb200_msa_join");
+		++g_NJoin;
+		g_MSAOrder = A;
+		g_MSAOrder.insert(g_MSAOrder.end(), B.begin(), B.end());
+		}
+	delete m_MSA;
+	m_MSA = MSAFromDevice(*this, g_MSAOrder);
+	g_TRefine += Now() - T0;
 	}

@@ -11,15 +11,10 @@
 #include "muscle.h"
 #include "pprog.h"
 #include "pairhmm.h"
+#include "mega.h"
 #include "../include/muscle_b200.h"
 #include <mutex>
 #include <unordered_map>
-
-// the reference's own (CPU) implementations, kept linked under C names by integration/Makefile
-extern "C" float REF_AlignPairFlat_SparsePost(const string &, const string &, string &, MySparseMx *);
-extern "C" void REF_CalcEADistMx(FILE *, MultiSequence *, vector<vector<float> > &, vector<MySparseMx *> *);
-extern "C" float REF_GetPostPairsAlignedFlat(PProg *, const string &, const MultiSequence &, const MultiSequence &,
-  const vector<uint> &, const vector<uint> &, vector<MySparseMx *> &);
 
 static mb200_ctx *g_PairCtx = 0;
 static std::mutex g_PairMutex;
@@ -32,6 +27,11 @@ static void CheckP(int rc, const char *What)
 
 static void EnsurePairCtx()
 	{
+	// calcpost.cpp:14 switches to the Mega emission functions when a .mega input is loaded; the
+	// engine implements the plain pair-HMM only and must not silently compute something else
+	if (Mega::m_Loaded)
+		Die("muscle_b200: Mega feature profiles (-mega / .mega input) are not implemented by the B200 engine; "
+		  "use the CPU build of muscle for this input");
 	if (g_PairCtx == 0)
 		{
 		int Device = 0;
@@ -120,8 +120,6 @@ float PProg::GetPostPairsAlignedFlat(const string &aProgressStr,
   const vector<uint> &SeqIndexes1, const vector<uint> &SeqIndexes2,
   vector<MySparseMx *> &SparsePosts)
 	{
-	if (getenv("MB200_CPU_PPROG") != 0)
-		return REF_GetPostPairsAlignedFlat(this, aProgressStr, MSA1, MSA2, SeqIndexes1, SeqIndexes2, SparsePosts);
 	const uint PairCount = SIZE(SeqIndexes1);
 	asserta(SIZE(SeqIndexes2) == PairCount);
 	asserta(SparsePosts.empty());
@@ -156,11 +154,6 @@ float PProg::GetPostPairsAlignedFlat(const string &aProgressStr,
 void CalcEADistMx(FILE *f, MultiSequence *sequences,
   vector<vector<float> > &DistMx, vector<MySparseMx *> *SparsePostVec)
 	{
-	if (getenv("MB200_CPU_EADIST") != 0)
-		{
-		REF_CalcEADistMx(f, sequences, DistMx, SparsePostVec);
-		return;
-		}
 	DistMx.clear();
 	const uint SeqCount = sequences->GetSeqCount();
 	DistMx.resize(SeqCount);
@@ -213,8 +206,6 @@ void CalcEADistMx(FILE *f, MultiSequence *sequences,
 float AlignPairFlat_SparsePost(const string &Label1, const string &Label2,
   string &Path, MySparseMx *SparsePost)
 	{
-	if (getenv("MB200_CPU_ALIGNPAIR") != 0)
-		return REF_AlignPairFlat_SparsePost(Label1, Label2, Path, SparsePost);
 	std::lock_guard<std::mutex> Guard(g_PairMutex);
 	EnsurePairCtx();
 	vector<string> L1(1, Label1), L2(1, Label2);

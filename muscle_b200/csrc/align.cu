@@ -1,17 +1,35 @@
-// align.cu -- posterior decoding on the device: max-sum DP with traceback (CalcAlnFlat) for batches
-// of stored pairs and for the column-posterior matrix of a progressive-alignment join (BuildPost).
+// align.cu -- posterior decoding on the device: the max-sum DP with traceback (CalcAlnFlat) for
+// batches of stored pairs, the column-posterior matrix of a progressive-alignment join (BuildPost),
+// and the device-resident multiple alignments that progressive alignment and refinement work on.
 //
 // Replaces CalcAlnFlat (calcalnflat.cpp:6-46) + Best3 (best3.h:5-28) + TraceBackFlat
-// (tracebackflat.cpp:3-37), MPCFlat::BuildPost (buildpostflat.cpp:18-105) and the arithmetic of
-// MPCFlat::AlignAlns (alnalnsflat.cpp:7-52).
+// (tracebackflat.cpp:3-37), MPCFlat::BuildPost (buildpostflat.cpp:18-105), MPCFlat::AlignAlns
+// (alnalnsflat.cpp:7-52) including Sequence::AddGapsPath (sequence.cpp:115-140) and
+// MultiSequence::Project (project.cpp:16-69) on position->column maps, i.e. the data path of
+// MPCFlat::ProgAln (progalnflat.cpp:41-71) and MPCFlat::RefineIter (refineflat.cpp:4-31).
 //
-// DP.  One CTA per problem, rows in sequence.  A row is  new[j] = max(old[j-1]+P[j], old[j], new[j-1])
-// which equals the running maximum over k<=j of max(old[k], old[k-1]+P[k]); the values are exact
-// maxima of the same fp32 sums the reference forms, so a block-wide prefix-max gives bit-identical
-// rows, and with old[j-1]+P, old[j] and new[j-1] known the traceback letter of every cell follows
-// from Best3's tie rule (B if B>=X and B>=Y; else Y if B>=X; else X if X>=Y else Y) independently.
+// Decoding DP (k_aln_wave).  One warp per problem; lane l owns 16 consecutive columns of a
+// 512-column strip and the rows are swept as an anti-diagonal wavefront (lane l is on row t-l at
+// step t, the left neighbour's value arrives by one shuffle), exactly the reference's recurrence
+//      new[j] = max3(old[j-1] + P[i][j], old[j], new[j-1])
+// evaluated with the same fp32 add and the same operands, so scores are bit-identical; the
+// traceback letter follows Best3's tie rule (B if B>=X and B>=Y; else Y if B>=X; else X if X>=Y else
+// Y) and is stored as 2 bits per cell (shared memory when it fits, else global), then walked by
+// lane 0 and reversed by the warp.  Round 1 used one CTA with 4+ barriers per row and a serial
+// traceback through global memory: 6.8 ms per 500x500 join; this is ~0.1 ms.
+//
+// BuildPost.  Every cell is a sum over (s,t) in the reference's s-major/t-minor order with at most
+// one term per (s,t); the order is kept per cell, everything else is parallel.  Phase 1 (k_bp_gather,
+// one thread per (row, s, t)) does the random gathers into the store and writes each needed sparse
+// row, mapped to columns of B, into a 16-entry staging slot; phase 2 (k_bp_apply, one warp per row,
+// accumulator row in shared memory) streams the slots through a cp.async double buffer and applies
+// them strictly in order, the entries of one sparse row in parallel.
 #include "engine.h"
+#include <cuda_pipeline.h>
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) \
@@ -20,12 +38,7 @@
 #define ENSURE(buf, bytes) do { if ((buf).ensure(bytes) != 0) \
 	return mb_fail(ctx, MB200_ENOMEM, "device allocation of %zu bytes failed (%s)", (size_t)(bytes), #buf); } while (0)
 
-#define ALN_THREADS 256
-
-// MB200_TRACE=1: wall-time split of mb200_align_groups, printed at process exit
-#include <chrono>
-#include <cstdlib>
-#include <cstdio>
+// MB200_TRACE=1: wall-time split of the join path, printed at process exit
 static bool g_trace = false;
 static double g_t[6] = { 0, 0, 0, 0, 0, 0 };
 static unsigned g_calls = 0;
@@ -35,163 +48,186 @@ static double now_s()
 	}
 static void trace_report()
 	{
-	fprintf(stderr, "[mb200 trace] align_groups x%u: host prep %.2f s, upload+memset %.2f s, gather %.2f s, apply %.2f s, "
-	  "decode DP %.2f s, download %.2f s\n", g_calls, g_t[0], g_t[1], g_t[2], g_t[3], g_t[4], g_t[5]);
+	fprintf(stderr, "[mb200 trace] joins x%u: maps %.2f s, BuildPost gather %.2f s, apply %.2f s, decode DP %.2f s, "
+	  "map update %.2f s, host %.2f s\n", g_calls, g_t[0], g_t[1], g_t[2], g_t[3], g_t[4], g_t[5]);
 	}
 #define TRACE_MARK(k) do { if (g_trace) { cudaStreamSynchronize(st); const double n_ = now_s(); g_t[k] += n_ - tmark; tmark = n_; } } while (0)
+static void trace_init()
+	{
+	static bool done = false;
+	if (done)
+		return;
+	done = true;
+	g_trace = getenv("MB200_TRACE") != nullptr;
+	if (g_trace)
+		atexit(trace_report);
+	}
 
+// =============================================================================================
+// decoding DP
+#define AW_C 16                      // columns per lane
+#define AW_W (32*AW_C)               // strip width
 struct AlnProblem
 	{
-	uint32_t LX, LY;
-	const float *dense;              // LX*LY row-major, or nullptr for sparse rows
-	const uint32_t *rowoff;          // sparse: CSR of the pair
-	const mb200_entry *entries;
-	char *tb;                        // (LX+1)*(LY+1) scratch
-	char *path;                      // LX+LY+1 output
+	uint32_t LX, LY, ld;             // ld: row pitch of dense (multiple of AW_C, padding zero)
+	const float *dense;              // LX rows x ld
+	uint32_t *tb;                    // traceback words [LX][nstrips*32] (global), unused when the launch keeps it in smem
+	float *edge;                     // 2*(LX+1) floats, strip hand-over (only read/written when LY > AW_W)
+	char *path;                      // LX+LY+1
 	float *score;
+	uint32_t *plen;                  // may be nullptr
 	};
 
-#define ALN_VPT 4            // columns per thread and pass: one pass covers 1024 columns
-
-__global__ void __launch_bounds__(ALN_THREADS)
-k_alnflat(const AlnProblem *probs)
+template <bool TB_SMEM>
+__global__ void __launch_bounds__(32)
+k_aln_wave(const AlnProblem *probs)
 	{
-	extern __shared__ float sh[];        // old[LY+1], prow[LY+1]
-	__shared__ float warpmax[ALN_THREADS/32];
-	__shared__ float carry_s;
+	extern __shared__ uint32_t tb_sm[];
 	const AlnProblem pr = probs[blockIdx.x];
-	const uint32_t LX = pr.LX, LY = pr.LY;
-	const uint32_t LY1 = LY + 1;
-	float *old = sh;
-	float *prow = sh + LY1;
-	const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-
-	for (uint32_t j = tid; j <= LY; j += ALN_THREADS)
+	const int lane = threadIdx.x;
+	const int LX = (int) pr.LX, LY = (int) pr.LY;
+	const int nstrips = (LY + AW_W - 1)/AW_W;
+	uint32_t *tb = TB_SMEM ? tb_sm : pr.tb;
+	float finalScore = 0.0f;
+	for (int strip = 0; strip < nstrips; ++strip)
 		{
-		old[j] = 0.0f;
-		prow[j] = 0.0f;
-		pr.tb[j] = 'Y';                                   // calcalnflat.cpp:15-19
-		}
-	__syncthreads();
-	for (uint32_t i = 1; i <= LX; ++i)
-		{
-		// stage P[i-1][*] into prow[1..LY]
-		if (pr.dense != nullptr)
+		const int j0 = strip*AW_W;
+		const int ncol = min(AW_W, LY - j0);
+		const int nl = (ncol + AW_C - 1)/AW_C;
+		const float *edgeIn = pr.edge + (size_t)(strip & 1)*(LX + 1);
+		float *edgeOut = pr.edge + (size_t)((strip + 1) & 1)*(LX + 1);
+		const bool hasIn = strip > 0, hasOut = strip + 1 < nstrips;
+		float old[AW_C];
+#pragma unroll
+		for (int c = 0; c < AW_C; ++c)
+			old[c] = 0.0f;                                   // row 0 (calcalnflat.cpp:15-19)
+		float outNew = 0.0f, prevRecv = 0.0f;
+		const float *src = pr.dense + j0 + lane*AW_C;
+		float4 nx0, nx1, nx2, nx3;
+		nx0 = nx1 = nx2 = nx3 = make_float4(0.f, 0.f, 0.f, 0.f);
+		if (lane == 0 && LX >= 1)
 			{
-			const float *src = pr.dense + (size_t)(i - 1)*LY;
-			for (uint32_t j = tid; j < LY; j += ALN_THREADS)
-				prow[j + 1] = src[j];
+			const float4 *q = reinterpret_cast<const float4 *>(src);
+			nx0 = q[0]; nx1 = q[1]; nx2 = q[2]; nx3 = q[3];
 			}
-		else
+		const int nsteps = LX + nl - 1;
+		// the lane that owns DP column LY (for the final score)
+		const int lastLane = (LY - 1 - j0)/AW_C, lastC = (LY - 1 - j0) % AW_C;
+		for (int t = 0; t < nsteps; ++t)
 			{
-			const uint32_t b = pr.rowoff[i - 1], e = pr.rowoff[i];
-			for (uint32_t k = b + tid; k < e; k += ALN_THREADS)
-				prow[pr.entries[k].col + 1] = pr.entries[k].p;
-			}
-		__syncthreads();
-		char *tbrow = pr.tb + (size_t) i*LY1;
-		if (tid == 0)
-			tbrow[0] = 'X';                                   // calcalnflat.cpp:25
-		float carry = 0.0f;                                   // new[0] = 0
-		for (uint32_t j0 = 1; j0 <= LY; j0 += ALN_THREADS*ALN_VPT)
-			{
-			const uint32_t jb = j0 + tid*ALN_VPT;             // this thread's first column
-			float B[ALN_VPT], X[ALN_VPT], r[ALN_VPT];
-			float left = jb <= LY ? old[jb - 1] : 0.0f;
-#pragma unroll
-			for (int q = 0; q < ALN_VPT; ++q)
+			const int i = t - lane + 1;                      // 1-based row
+			float recv = __shfl_up_sync(MB_FULL, outNew, 1);
+			if (lane == 0)
+				recv = (hasIn && i >= 0 && i <= LX) ? edgeIn[i] : 0.0f;
+			const bool valid = i >= 1 && i <= LX && lane < nl;
+			float p[AW_C];
+			p[0] = nx0.x; p[1] = nx0.y; p[2] = nx0.z; p[3] = nx0.w; p[4] = nx1.x; p[5] = nx1.y; p[6] = nx1.z; p[7] = nx1.w;
+			p[8] = nx2.x; p[9] = nx2.y; p[10] = nx2.z; p[11] = nx2.w; p[12] = nx3.x; p[13] = nx3.y; p[14] = nx3.z; p[15] = nx3.w;
+			// prefetch the row this lane works on in the next step
+			if (lane < nl && i + 1 >= 1 && i + 1 <= LX)
 				{
-				const uint32_t j = jb + q;
-				const bool in = j <= LY;
-				X[q] = in ? old[j] : 0.0f;
-				B[q] = in ? __fadd_rn(left, prow[j]) : 0.0f;
-				left = X[q];
-				const float v = fmaxf(B[q], X[q]);
-				r[q] = q == 0 ? v : fmaxf(r[q > 0 ? q - 1 : 0], v);
+				const float4 *q = reinterpret_cast<const float4 *>(src + (size_t) i*pr.ld);
+				nx0 = q[0]; nx1 = q[1]; nx2 = q[2]; nx3 = q[3];
 				}
-			// inclusive prefix max of the per-thread maxima across the block
-			float run = r[ALN_VPT - 1];
-#pragma unroll
-			for (int o = 1; o < 32; o <<= 1)
+			if (valid)
 				{
-				const float t = __shfl_up_sync(MB_FULL, run, o);
-				if (lane >= (uint32_t) o)
-					run = fmaxf(run, t);
-				}
-			if (lane == 31)
-				warpmax[wid] = run;
-			__syncthreads();
-			float pre = carry;                                // max of everything left of this pass
-			for (uint32_t w = 0; w < wid; ++w)
-				pre = fmaxf(pre, warpmax[w]);
-			float excl = __shfl_up_sync(MB_FULL, run, 1);     // new[jb-1] inside the warp
-			excl = lane == 0 ? pre : fmaxf(excl, pre);
-			float Y = excl;
+				float Y = recv;                                // new[i][first col - 1]
+				float diag = prevRecv;                         // new[i-1][first col - 1]
+				uint32_t word = 0;
 #pragma unroll
-			for (int q = 0; q < ALN_VPT; ++q)
-				{
-				const uint32_t j = jb + q;
-				const float nw = fmaxf(r[q], excl);               // new[j]
-				if (j <= LY)
+				for (int c = 0; c < AW_C; ++c)
 					{
-					char t;
-					if (B[q] >= X[q])
-						t = (B[q] >= Y) ? 'B' : 'Y';                 // best3.h:5-28 tie order
-					else
-						t = (X[q] >= Y) ? 'X' : 'Y';
-					tbrow[j] = t;
-					// old[] must stay the previous row until every thread has read it: park in prow[]
-					prow[j] = nw;
+					const float B = __fadd_rn(diag, p[c]);       // calcalnflat.cpp:31-37
+					const float X = old[c];
+					const float nw = fmaxf(fmaxf(B, X), Y);
+					const uint32_t code = (B >= X) ? ((B >= Y) ? 0u : 2u) : ((X >= Y) ? 1u : 2u);    // best3.h:5-28
+					word |= code << (2*c);
+					diag = X;
+					old[c] = nw;
+					Y = nw;
+					if (c == lastC && lane == lastLane && i == LX && strip == nstrips - 1)
+						finalScore = nw;
 					}
-				Y = nw;
+				outNew = Y;
+				tb[((size_t)(i - 1)*nstrips + strip)*32 + lane] = word;
+				if (hasOut && lane == 31)
+					edgeOut[i] = outNew;
 				}
-			if (j0 + ALN_THREADS*ALN_VPT <= LY)
-				{
-				// another pass follows: hand the running maximum over
-				if (tid == ALN_THREADS - 1)
-					carry_s = Y;
-				__syncthreads();
-				carry = carry_s;
-				}
+			prevRecv = recv;
 			}
-		__syncthreads();
-		for (uint32_t j = tid + 1; j <= LY; j += ALN_THREADS)
-			{
-			old[j] = prow[j];
-			prow[j] = 0.0f;
-			}
-		__syncthreads();
+		if (hasOut && lane == 31)
+			edgeOut[0] = 0.0f;
+		__syncwarp();
 		}
-	if (tid == 0)
+	finalScore = __shfl_sync(MB_FULL, finalScore, (LY - 1 - (nstrips - 1)*AW_W)/AW_C);
+	__syncwarp();
+	// traceback (tracebackflat.cpp:3-37): TB(0,j) = 'Y', TB(i,0) = 'X'
+	uint32_t n = 0;
+	if (lane == 0)
 		{
-		*pr.score = old[LY];
-		// tracebackflat.cpp:3-37
-		uint32_t n = 0;
-		int64_t i = LX, j = LY;
+		int i = LX, j = LY;
+		int curRow = -1, curIdx = -1;
+		uint32_t w = 0;
 		while (i != 0 || j != 0)
 			{
-			const char t = pr.tb[(size_t) i*LY1 + (size_t) j];
+			char t;
+			if (i == 0)
+				t = 'Y';
+			else if (j == 0)
+				t = 'X';
+			else
+				{
+				const int jj = j - 1;
+				const int idx = (jj/AW_W)*32 + (jj % AW_W)/AW_C;
+				if (i != curRow || idx != curIdx)
+					{
+					w = tb[(size_t)(i - 1)*nstrips*32 + idx];
+					curRow = i; curIdx = idx;
+					}
+				const uint32_t code = (w >> (2*(jj % AW_C))) & 3u;
+				t = code == 0 ? 'B' : (code == 1 ? 'X' : 'Y');
+				}
 			pr.path[n++] = t;
 			if (t == 'B') { --i; --j; }
 			else if (t == 'X') --i;
 			else --j;
 			}
-		for (uint32_t a = 0, b = n; a + 1 < b; ++a, --b)
-			{
-			const char t = pr.path[a]; pr.path[a] = pr.path[b - 1]; pr.path[b - 1] = t;
-			}
 		pr.path[n] = 0;
+		*pr.score = finalScore;
+		if (pr.plen)
+			*pr.plen = n;
+		}
+	n = __shfl_sync(MB_FULL, n, 0);
+	__syncwarp();
+	for (uint32_t a = lane; a < n/2; a += 32)
+		{
+		const char x = pr.path[a], y = pr.path[n - 1 - a];
+		pr.path[a] = y; pr.path[n - 1 - a] = x;
 		}
 	}
 
-// ---------------------------------------------------------------------------------------------
-// BuildPost: one 8-lane group owns one column (row of Post) of alignment A and walks (s,t) in the
-// reference's s-major, t-minor order; a cell receives at most one term per (s,t), so the owner's
-// sequential adds reproduce the reference's fp32 sums exactly.
+// dense copy of stored sparse pairs for the batched pair decoder: one warp per (problem,row)
+struct DensifyJob { const uint32_t *rowoff; const mb200_entry *entries; float *dense; uint32_t LX, ld; };
+__global__ void k_densify(const DensifyJob *jobs, uint32_t njobs, uint32_t maxrows)
+	{
+	const uint32_t warp = (blockIdx.x*blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+	const uint32_t job = warp/maxrows, row = warp % maxrows;
+	if (job >= njobs)
+		return;
+	const DensifyJob J = jobs[job];
+	if (row >= J.LX)
+		return;
+	float *dst = J.dense + (size_t) row*J.ld;
+	for (uint32_t e = J.rowoff[row] + lane; e < J.rowoff[row + 1]; e += 32)
+		dst[J.entries[e].col] = J.entries[e].p;
+	}
+
+// =============================================================================================
+// BuildPost
 struct BuildPostParams
 	{
 	uint32_t n;                                   // sequences in the store
-	uint32_t na, nb, cols_a, cols_b;
+	uint32_t na, nb, cols_a, cols_b, ld;          // ld: row pitch of post
 	const uint32_t *ids_a, *ids_b;
 	const int32_t *col2pos_a;                     // [na][cols_a], -1 = gap
 	const uint32_t *p2c_b;                        // concatenated pos->col maps of B
@@ -199,69 +235,34 @@ struct BuildPostParams
 	const uint64_t *rowbase;  const uint32_t *rowoff;  const mb200_entry *entries;
 	const uint64_t *trbase;   const uint32_t *troff;   const mb200_entry *trentries;
 	const uint64_t *entbase;
-	float *post;                                  // cols_a*cols_b, zeroed
+	float *post;                                  // cols_a x ld, zeroed
 	};
 
-__global__ void __launch_bounds__(128)
-k_buildpost(const BuildPostParams P)
-	{
-	const uint32_t grp = (blockIdx.x*blockDim.x + threadIdx.x) >> 3;      // Post row = column of A
-	const uint32_t gl = threadIdx.x & 7;
-	if (grp >= P.cols_a)
-		return;
-	float *prow = P.post + (size_t) grp*P.cols_b;
-	const unsigned gmask = 0xffu << ((threadIdx.x & 31) & ~7u);
-	for (uint32_t s = 0; s < P.na; ++s)
-		{
-		const int32_t pos = P.col2pos_a[(size_t) s*P.cols_a + grp];
-		if (pos < 0)
-			continue;
-		const uint32_t a = P.ids_a[s];
-		for (uint32_t t = 0; t < P.nb; ++t)
-			{
-			const uint32_t b = P.ids_b[t];
-			const uint32_t *ro;
-			const mb200_entry *en;
-			if (a < b)
-				{
-				const uint32_t q = (uint32_t)((uint64_t) a*P.n - (uint64_t) a*(a + 1)/2 + (b - a - 1));
-				ro = P.rowoff + P.rowbase[q]; en = P.entries + P.entbase[q];
-				}
-			else
-				{
-				const uint32_t q = (uint32_t)((uint64_t) b*P.n - (uint64_t) b*(b + 1)/2 + (a - b - 1));
-				ro = P.troff + P.trbase[q]; en = P.trentries + P.entbase[q];
-				}
-			const uint32_t e0 = ro[pos], e1 = ro[pos + 1];
-			const uint32_t *p2c = P.p2c_b + P.p2c_b_off[t];
-			for (uint32_t e = e0 + gl; e < e1; e += 8)
-				{
-				const mb200_entry v = en[e];
-				const uint32_t c2 = p2c[v.col];
-				prow[c2] = __fadd_rn(prow[c2], v.p);          // += w1*w2*P with unit weights
-				}
-			__syncwarp(gmask);
-			}
-		}
-	}
-
 #define BP_WARPS 4
-#define BP_W 16           // staged entries per sparse row (rows are 7.2 +- 3 long: 25 % exceed 8, ~0.1 % exceed 16)
+#define BP_W 16           // staged entries per sparse row (rows are 7.2 +- 3 long: ~0.1 % exceed 16)
+#define BP_G 16           // (s,t) steps per staged group
 
-// ---------------------------------------------------------------------------------------------
-// Two-phase BuildPost (default).  The direct formulation (k_buildpost: one lane group per row walking all (s,t)) is
-// latency bound: every (s,t) step chains 4-5 dependent random loads into the 10 GB store and only
-// cols_a groups exist (C3 trace: 44 ms per AlignAlns call, 49 s of a 110 s `muscle -align`).  Here the random gathers are done by a
-// massively parallel pre-pass -- one THREAD per (row, s, t) copies the <= BP_W entries of the needed
-// sparse row, already mapped to columns of B, into a dense staging slot -- and the order-sensitive
-// accumulation then streams the staging area with coalesced loads.  The fp32 sum order of the
-// reference (s-major, t-minor) is unchanged, so the result stays bit-identical.
 struct BpStage
 	{
 	uint2   *slots;      // [row][s_local][t][BP_W]  (column of B, bits of P)
 	uint8_t *cnt;        // [row][s_local][t]; 255 = row longer than BP_W (applied by direct gather)
 	uint32_t s_lo, s_n;  // batch of sequences of A
 	};
+
+__device__ __forceinline__ void bp_operand(const BuildPostParams &P, uint32_t a, uint32_t b, const uint32_t *&ro,
+  const mb200_entry *&en)
+	{
+	if (a < b)
+		{
+		const uint32_t q = (uint32_t)((uint64_t) a*P.n - (uint64_t) a*(a + 1)/2 + (b - a - 1));
+		ro = P.rowoff + P.rowbase[q]; en = P.entries + P.entbase[q];
+		}
+	else
+		{
+		const uint32_t q = (uint32_t)((uint64_t) b*P.n - (uint64_t) b*(b + 1)/2 + (a - b - 1));
+		ro = P.troff + P.trbase[q]; en = P.trentries + P.entbase[q];
+		}
+	}
 
 __global__ void __launch_bounds__(256)
 k_bp_gather(const BuildPostParams P, const BpStage G)
@@ -278,19 +279,9 @@ k_bp_gather(const BuildPostParams P, const BpStage G)
 		uint32_t n = 0;
 		if (pos >= 0)
 			{
-			const uint32_t a = P.ids_a[s], b = P.ids_b[t];
 			const uint32_t *ro;
 			const mb200_entry *en;
-			if (a < b)
-				{
-				const uint32_t q = (uint32_t)((uint64_t) a*P.n - (uint64_t) a*(a + 1)/2 + (b - a - 1));
-				ro = P.rowoff + P.rowbase[q]; en = P.entries + P.entbase[q];
-				}
-			else
-				{
-				const uint32_t q = (uint32_t)((uint64_t) b*P.n - (uint64_t) b*(b + 1)/2 + (a - b - 1));
-				ro = P.troff + P.trbase[q]; en = P.trentries + P.entbase[q];
-				}
+			bp_operand(P, P.ids_a[s], P.ids_b[t], ro, en);
 			const uint32_t e0 = ro[pos];
 			n = ro[pos + 1] - e0;
 			if (n <= BP_W)
@@ -310,23 +301,27 @@ k_bp_gather(const BuildPostParams P, const BpStage G)
 		}
 	}
 
+// One warp per row (column of alignment A).  The (s,t) steps of one s are consumed in groups of
+// BP_G: while group g is applied, the 2 KB of slots of group g+1 are already on their way into the
+// other half of a shared-memory double buffer (cp.async), so the ordered accumulation never waits
+// on HBM; inside a step the <= 16 entries of the sparse row go to distinct columns and are added
+// by one lane each.
 __global__ void __launch_bounds__(32*BP_WARPS)
 k_bp_apply(const BuildPostParams P, const BpStage G)
 	{
 	extern __shared__ __align__(16) unsigned char bp_smem[];
 	const uint32_t wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	const uint32_t row = blockIdx.x*BP_WARPS + wib;
+	const size_t acc_bytes = ((size_t) BP_WARPS*P.cols_b*sizeof(float) + 15) & ~(size_t) 15;
 	float *acc = reinterpret_cast<float *>(bp_smem) + (size_t) wib*P.cols_b;
-	// per-warp copy of the 32 staged rows of the current chunk (the ordered apply must not wait on
-	// one global load per (s,t))
-	uint2 *stage = reinterpret_cast<uint2 *>(bp_smem + (((size_t) BP_WARPS*P.cols_b*sizeof(float) + 15) & ~(size_t) 15))
-	  + (size_t) wib*32*BP_W;
+	uint2 *stage = reinterpret_cast<uint2 *>(bp_smem + acc_bytes) + (size_t) wib*2*BP_G*BP_W;
 	if (row >= P.cols_a)
 		return;
-	float *prow = P.post + (size_t) row*P.cols_b;
+	float *prow = P.post + (size_t) row*P.ld;
 	for (uint32_t c = lane; c < P.cols_b; c += 32)
 		acc[c] = prow[c];
 	__syncwarp();
+	const uint32_t ngroups = (P.nb + BP_G - 1)/BP_G;
 	for (uint32_t sl = 0; sl < G.s_n; ++sl)
 		{
 		const uint32_t s = G.s_lo + sl;
@@ -334,52 +329,66 @@ k_bp_apply(const BuildPostParams P, const BpStage G)
 		if (pos < 0)
 			continue;
 		const uint64_t base = ((uint64_t) row*G.s_n + sl)*P.nb;
-		for (uint32_t t0 = 0; t0 < P.nb; t0 += 32)
+		// prologue: group 0 in flight
+		uint32_t cntNext = 0;
+		{
+		const uint32_t nt = min((uint32_t) BP_G, P.nb);
+		if (lane < nt)
+			cntNext = G.cnt[base + lane];
+		const uint4 *src = reinterpret_cast<const uint4 *>(G.slots + base*BP_W);
+		uint4 *dst = reinterpret_cast<uint4 *>(stage);
+		for (uint32_t q = lane; q < nt*(BP_W/2); q += 32)
+			__pipeline_memcpy_async(dst + q, src + q, 16);
+		__pipeline_commit();
+		}
+		for (uint32_t g = 0; g < ngroups; ++g)
 			{
-			const uint32_t t = t0 + lane;
-			const uint32_t n = t < P.nb ? (uint32_t) G.cnt[base + t] : 0u;
-			const uint32_t any = __ballot_sync(MB_FULL, n != 0);
-			if (any == 0)
-				continue;
-			if (n != 0 && n != 255)
+			const uint32_t t0 = g*BP_G;
+			const uint32_t nt = min((uint32_t) BP_G, P.nb - t0);
+			const uint32_t cntCur = cntNext;
+			cntNext = 0;
+			if (g + 1 < ngroups)
 				{
-				const uint4 *src = reinterpret_cast<const uint4 *>(G.slots + (base + t)*BP_W);
-				uint4 *dst = reinterpret_cast<uint4 *>(stage + lane*BP_W);
-#pragma unroll
-				for (int k = 0; k < (int)(BP_W*sizeof(uint2)/sizeof(uint4)); ++k)
-					dst[k] = src[k];
+				const uint32_t t1 = t0 + BP_G;
+				const uint32_t nt1 = min((uint32_t) BP_G, P.nb - t1);
+				if (lane < nt1)
+					cntNext = G.cnt[base + t1 + lane];
+				const uint4 *src = reinterpret_cast<const uint4 *>(G.slots + (base + t1)*BP_W);
+				uint4 *dst = reinterpret_cast<uint4 *>(stage + (size_t)((g + 1) & 1)*BP_G*BP_W);
+				for (uint32_t q = lane; q < nt1*(BP_W/2); q += 32)
+					__pipeline_memcpy_async(dst + q, src + q, 16);
 				}
+			__pipeline_commit();
+			__pipeline_wait_prior(1);                          // group g has landed
 			__syncwarp();
-			uint32_t rest = any;
+			const uint2 *cur = stage + (size_t)(g & 1)*BP_G*BP_W;
+			uint32_t rest = __ballot_sync(MB_FULL, lane < nt && cntCur != 0);
+			// 1-deep software pipeline over the steps of the group: the next step's entry is fetched
+			// from the stage before the current one is added
+			uint32_t l = rest ? (uint32_t) __ffs(rest) - 1 : 0;
+			uint32_t nl = __shfl_sync(MB_FULL, cntCur, l);
+			uint2 v = make_uint2(0u, 0u);
+			if (rest && nl != 255 && lane < nl)
+				v = cur[l*BP_W + lane];
 			while (rest)
 				{
-				const uint32_t l = __ffs(rest) - 1;
 				rest &= rest - 1;
-				const uint32_t nl = __shfl_sync(MB_FULL, n, l);
+				const uint32_t l2 = rest ? (uint32_t) __ffs(rest) - 1 : 0;
+				const uint32_t nl2 = __shfl_sync(MB_FULL, cntCur, l2);
+				uint2 v2 = make_uint2(0u, 0u);
+				if (rest && nl2 != 255 && lane < nl2)
+					v2 = cur[l2*BP_W + lane];
 				if (nl != 255)
 					{
 					if (lane < nl)
-						{
-						const uint2 v = stage[l*BP_W + lane];
-						acc[v.x] = __fadd_rn(acc[v.x], __uint_as_float(v.y));     // += w1*w2*P, unit weights
-						}
+						acc[v.x] = __fadd_rn(acc[v.x], __uint_as_float(v.y));        // += w1*w2*P, unit weights
 					}
 				else if (lane == 0)
 					{
 					// rare: more than BP_W entries in the sparse row -> gather directly, still in order
-					const uint32_t a = P.ids_a[s], b = P.ids_b[t0 + l];
 					const uint32_t *ro;
 					const mb200_entry *en;
-					if (a < b)
-						{
-						const uint32_t q = (uint32_t)((uint64_t) a*P.n - (uint64_t) a*(a + 1)/2 + (b - a - 1));
-						ro = P.rowoff + P.rowbase[q]; en = P.entries + P.entbase[q];
-						}
-					else
-						{
-						const uint32_t q = (uint32_t)((uint64_t) b*P.n - (uint64_t) b*(b + 1)/2 + (a - b - 1));
-						ro = P.troff + P.trbase[q]; en = P.trentries + P.entbase[q];
-						}
+					bp_operand(P, P.ids_a[s], P.ids_b[t0 + l], ro, en);
 					const uint32_t *p2c = P.p2c_b + P.p2c_b_off[t0 + l];
 					for (uint32_t e = ro[pos]; e < ro[pos + 1]; ++e)
 						{
@@ -388,11 +397,306 @@ k_bp_apply(const BuildPostParams P, const BpStage G)
 						}
 					}
 				__syncwarp();
+				l = l2; nl = nl2; v = v2;
 				}
+			__syncwarp();
 			}
+		__pipeline_wait_prior(0);
 		}
 	for (uint32_t c = lane; c < P.cols_b; c += 32)
 		prow[c] = acc[c];
+	}
+
+// =============================================================================================
+// device-resident MSAs: position -> column maps
+struct MsaJob
+	{
+	uint32_t na, nb;                         // members: ids[0..na) = A, ids[na..na+nb) = B
+	const uint32_t *ids;
+	const uint64_t *seqoff;                  // residue offset of every sequence (layout of p2c)
+	const uint32_t *seqlen;
+	uint32_t *p2c;                           // all sequences
+	uint32_t *mark;                          // [2][cap]: column occupancy of A / B, then remap
+	uint32_t cap;                            // >= old column counts
+	uint32_t old_cols_a, old_cols_b;
+	uint32_t *dims;                          // [0] cols_a, [1] cols_b after projection
+	// filled for the maps kernel
+	int32_t *c2p_a; uint32_t cols_a;         // [na][cols_a]
+	uint32_t *p2c_b; const uint64_t *boff;   // concatenated
+	// update
+	const char *path; const uint32_t *plen;
+	uint32_t *map;                           // [2][cap]: projected column -> column of the joined MSA
+	};
+
+__global__ void k_msa_identity(uint64_t total, const uint64_t *__restrict__ seqoff, uint32_t nseq, uint32_t *__restrict__ p2c)
+	{
+	// p2c[off[s] + i] = i : find s by binary search over the offsets
+	for (uint64_t r = blockIdx.x*(uint64_t) blockDim.x + threadIdx.x; r < total; r += (uint64_t) gridDim.x*blockDim.x)
+		{
+		uint32_t lo = 0, hi = nseq;
+		while (hi - lo > 1)
+			{
+			const uint32_t mid = (lo + hi) >> 1;
+			if (seqoff[mid] <= r) lo = mid; else hi = mid;
+			}
+		p2c[r] = (uint32_t)(r - seqoff[lo]);
+		}
+	}
+
+// grid (ceil(Lmax/256), na+nb)
+__global__ void k_msa_mark(const MsaJob J)
+	{
+	const uint32_t m = blockIdx.y;
+	const uint32_t s = J.ids[m];
+	const uint32_t L = J.seqlen[s];
+	uint32_t *mark = J.mark + (m < J.na ? 0 : J.cap);
+	const uint32_t *p = J.p2c + J.seqoff[s];
+	for (uint32_t i = blockIdx.x*blockDim.x + threadIdx.x; i < L; i += gridDim.x*blockDim.x)
+		mark[p[i]] = 1u;
+	}
+
+// grid 2 (A, B), 1024 threads: exclusive scan of the occupancy marks -> projected column index
+// (MultiSequence::Project drops all-gap columns, project.cpp:41-66)
+__global__ void __launch_bounds__(1024)
+k_msa_remap(const MsaJob J)
+	{
+	__shared__ uint32_t wsum[32];
+	__shared__ uint32_t carry_s;
+	const uint32_t which = blockIdx.x;
+	uint32_t *mark = J.mark + which*J.cap;
+	const uint32_t ncol = which == 0 ? J.old_cols_a : J.old_cols_b;
+	const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+	if (threadIdx.x == 0)
+		carry_s = 0;
+	__syncthreads();
+	for (uint32_t c0 = 0; c0 < ncol; c0 += 1024)
+		{
+		const uint32_t c = c0 + threadIdx.x;
+		const uint32_t f = c < ncol ? mark[c] : 0u;
+		uint32_t v = f;
+#pragma unroll
+		for (int o = 1; o < 32; o <<= 1)
+			{
+			const uint32_t t = __shfl_up_sync(MB_FULL, v, o);
+			if (lane >= (uint32_t) o)
+				v += t;
+			}
+		if (lane == 31)
+			wsum[wid] = v;
+		__syncthreads();
+		uint32_t pre = carry_s;
+		for (uint32_t w = 0; w < wid; ++w)
+			pre += wsum[w];
+		if (c < ncol)
+			mark[c] = pre + v - f;                    // exclusive
+		__syncthreads();
+		if (threadIdx.x == 1023)
+			carry_s = pre + v;
+		__syncthreads();
+		}
+	if (threadIdx.x == 0)
+		J.dims[which] = carry_s;
+	}
+
+// grid (ceil(Lmax/256), na+nb): col->pos of the projected A, pos->col of the projected B
+__global__ void k_msa_maps(const MsaJob J)
+	{
+	const uint32_t m = blockIdx.y;
+	const uint32_t s = J.ids[m];
+	const uint32_t L = J.seqlen[s];
+	const uint32_t *p = J.p2c + J.seqoff[s];
+	if (m < J.na)
+		{
+		const uint32_t *remap = J.mark;
+		int32_t *c2p = J.c2p_a + (size_t) m*J.cols_a;
+		for (uint32_t i = blockIdx.x*blockDim.x + threadIdx.x; i < L; i += gridDim.x*blockDim.x)
+			c2p[remap[p[i]]] = (int32_t) i;
+		}
+	else
+		{
+		const uint32_t *remap = J.mark + J.cap;
+		uint32_t *dst = J.p2c_b + J.boff[m - J.na];
+		for (uint32_t i = blockIdx.x*blockDim.x + threadIdx.x; i < L; i += gridDim.x*blockDim.x)
+			dst[i] = remap[p[i]];
+		}
+	}
+
+// one block: column of the joined MSA for every projected column of A ('B' or 'X' letters of the
+// path, in order) and of B ('B' or 'Y') -- what Sequence::AddGapsPath does to a row (sequence.cpp:115-140)
+__global__ void __launch_bounds__(1024)
+k_msa_pathmap(const MsaJob J)
+	{
+	__shared__ uint32_t wsumA[32], wsumB[32];
+	__shared__ uint32_t carryA, carryB;
+	const uint32_t n = *J.plen;
+	const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+	if (threadIdx.x == 0)
+		{
+		carryA = 0; carryB = 0;
+		}
+	__syncthreads();
+	for (uint32_t q0 = 0; q0 < n; q0 += 1024)
+		{
+		const uint32_t q = q0 + threadIdx.x;
+		const char t = q < n ? J.path[q] : 0;
+		const uint32_t fa = (t == 'B' || t == 'X') ? 1u : 0u;
+		const uint32_t fb = (t == 'B' || t == 'Y') ? 1u : 0u;
+		uint32_t va = fa, vb = fb;
+#pragma unroll
+		for (int o = 1; o < 32; o <<= 1)
+			{
+			const uint32_t ta = __shfl_up_sync(MB_FULL, va, o);
+			const uint32_t tb = __shfl_up_sync(MB_FULL, vb, o);
+			if (lane >= (uint32_t) o)
+				{
+				va += ta; vb += tb;
+				}
+			}
+		if (lane == 31)
+			{
+			wsumA[wid] = va; wsumB[wid] = vb;
+			}
+		__syncthreads();
+		uint32_t pa = carryA, pb = carryB;
+		for (uint32_t w = 0; w < wid; ++w)
+			{
+			pa += wsumA[w]; pb += wsumB[w];
+			}
+		if (fa)
+			J.map[pa + va - 1] = q;
+		if (fb)
+			J.map[J.cap + pb + vb - 1] = q;
+		__syncthreads();
+		if (threadIdx.x == 1023)
+			{
+			carryA = pa + va; carryB = pb + vb;
+			}
+		__syncthreads();
+		}
+	}
+
+// grid (ceil(Lmax/256), na+nb): p2c[s][i] = map[remap[p2c[s][i]]]
+__global__ void k_msa_update(const MsaJob J)
+	{
+	const uint32_t m = blockIdx.y;
+	const uint32_t s = J.ids[m];
+	const uint32_t L = J.seqlen[s];
+	uint32_t *p = J.p2c + J.seqoff[s];
+	const uint32_t off = m < J.na ? 0 : J.cap;
+	for (uint32_t i = blockIdx.x*blockDim.x + threadIdx.x; i < L; i += gridDim.x*blockDim.x)
+		p[i] = J.map[off + J.mark[off + p[i]]];
+	}
+
+// =============================================================================================
+// host side
+static inline size_t al256(size_t b) { return (b + 255)/256*256; }
+
+struct JoinBufs                       // carved out of ctx->d_join
+	{
+	float *post; uint32_t ld;
+	uint32_t *tb; float *edge; char *path; float *score; uint32_t *plen; AlnProblem *prob;
+	};
+
+// BuildPost + decoding DP of groups whose maps are already on the device.  Leaves path / plen /
+// score on the device (JoinBufs) and does NOT synchronise.
+static int join_core(mb200_ctx *ctx, uint32_t na, uint32_t nb, const uint32_t *d_ida, const uint32_t *d_idb,
+  const int32_t *d_c2pa, const uint32_t *d_p2cb, const uint64_t *d_boff, uint32_t cols_a, uint32_t cols_b,
+  char *scratch, size_t scratch_bytes, JoinBufs &B, double &tmark)
+	{
+	cudaStream_t st = ctx->stream;
+	const uint32_t ld = (cols_b + AW_C - 1)/AW_C*AW_C;
+	const uint32_t nstrips = (cols_b + AW_W - 1)/AW_W;
+	const size_t post_bytes = (size_t) cols_a*ld*sizeof(float);
+	const size_t tbw = (size_t) cols_a*nstrips*32*sizeof(uint32_t);
+	const bool tb_smem = tbw <= 200*1024;
+	char *p = scratch;
+	B.post = (float *) p;            p += al256(post_bytes);
+	B.tb = (uint32_t *) p;           p += tb_smem ? 256 : al256(tbw);
+	B.edge = (float *) p;            p += al256(2*((size_t) cols_a + 1)*sizeof(float));
+	B.path = p;                      p += al256((size_t) cols_a + cols_b + 16);
+	B.score = (float *) p;           p += 256;
+	B.plen = (uint32_t *) p;         p += 256;
+	B.prob = (AlnProblem *) p;       p += 256;
+	B.ld = ld;
+	if ((size_t)(p - scratch) > scratch_bytes)
+		return mb_fail(ctx, MB200_EINVAL, "join scratch too small");
+	CU(cudaMemsetAsync(B.post, 0, post_bytes, st));
+
+	BuildPostParams P;
+	P.n = ctx->nseq; P.na = na; P.nb = nb; P.cols_a = cols_a; P.cols_b = cols_b; P.ld = ld;
+	P.ids_a = d_ida; P.ids_b = d_idb; P.col2pos_a = d_c2pa; P.p2c_b = d_p2cb; P.p2c_b_off = d_boff;
+	P.rowbase = (const uint64_t *) ctx->d_rowbase.p; P.rowoff = (const uint32_t *) ctx->d_rowoff.p;
+	P.entries = (const mb200_entry *) ctx->d_entries.p;
+	P.trbase = (const uint64_t *) ctx->d_tr_rowbase.p; P.troff = (const uint32_t *) ctx->d_tr_rowoff.p;
+	P.trentries = (const mb200_entry *) ctx->d_tr_entries.p;
+	P.entbase = (const uint64_t *) ctx->d_entbase.p;
+	P.post = B.post;
+	// the accumulator rows of BP_WARPS warps + their cp.async double buffers must fit in shared memory
+	const size_t acc_smem = (((size_t) BP_WARPS*cols_b*sizeof(float) + 15) & ~(size_t) 15) + (size_t) BP_WARPS*2*BP_G*BP_W*sizeof(uint2);
+	if (acc_smem > 220*1024)
+		return mb_fail(ctx, MB200_EOVERFLOW, "alignment with %u columns too wide for the BuildPost kernel", cols_b);
+	// batches of sequences of A sized so that the staging area stays below ~1 GB
+	const uint64_t per_s = (uint64_t) cols_a*nb*(BP_W*sizeof(uint2) + 1);
+	const uint32_t sb = (uint32_t) std::max<uint64_t>(1, std::min<uint64_t>(na, (1024ull << 20)/std::max<uint64_t>(per_s, 1)));
+	const uint64_t nslots = (uint64_t) cols_a*sb*nb;
+	ENSURE(ctx->d_stage, nslots*BP_W*sizeof(uint2) + nslots + 256);
+	BpStage G;
+	G.slots = (uint2 *) ctx->d_stage.p;
+	G.cnt = (uint8_t *)(G.slots + nslots*BP_W);
+	CU(cudaFuncSetAttribute(k_bp_apply, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) acc_smem));
+	for (uint32_t s_lo = 0; s_lo < na; s_lo += sb)
+		{
+		G.s_lo = s_lo;
+		G.s_n = std::min(sb, na - s_lo);
+		const uint64_t total = (uint64_t) cols_a*G.s_n*nb;
+		const uint32_t gblocks = (uint32_t) std::min<uint64_t>((total + 255)/256, (uint64_t) ctx->prop.multiProcessorCount*32);
+		k_bp_gather<<<gblocks, 256, 0, st>>>(P, G);
+		TRACE_MARK(1);
+		k_bp_apply<<<(cols_a + BP_WARPS - 1)/BP_WARPS, 32*BP_WARPS, acc_smem, st>>>(P, G);
+		TRACE_MARK(2);
+		ctx->stats.kernel_launches += 2;
+		}
+	CU(cudaGetLastError());
+	AlnProblem pr;
+	pr.LX = cols_a; pr.LY = cols_b; pr.ld = ld; pr.dense = B.post; pr.tb = B.tb; pr.edge = B.edge;
+	pr.path = B.path; pr.score = B.score; pr.plen = B.plen;
+	CU(cudaMemcpyAsync(B.prob, &pr, sizeof pr, cudaMemcpyHostToDevice, st));
+	if (tb_smem)
+		{
+		CU(cudaFuncSetAttribute(k_aln_wave<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) std::max<size_t>(tbw, 16)));
+		k_aln_wave<true><<<1, 32, tbw, st>>>(B.prob);
+		}
+	else
+		k_aln_wave<false><<<1, 32, 0, st>>>(B.prob);
+	CU(cudaGetLastError());
+	ctx->stats.kernel_launches++;
+	TRACE_MARK(3);
+	return MB200_OK;
+	}
+
+static size_t join_scratch_bytes(uint32_t cols_a, uint32_t cols_b)
+	{
+	const uint32_t ld = (cols_b + AW_C - 1)/AW_C*AW_C;
+	const uint32_t nstrips = (cols_b + AW_W - 1)/AW_W;
+	return al256((size_t) cols_a*ld*4) + al256((size_t) cols_a*nstrips*32*4) + al256(2*((size_t) cols_a + 1)*4)
+	  + al256((size_t) cols_a + cols_b + 16) + 4*256;
+	}
+
+static int need_store_for_joins(mb200_ctx *ctx, const char *who)
+	{
+	if (!ctx->store_valid || !ctx->store_allpairs)
+		return mb_fail(ctx, MB200_EINVAL, "%s: the store must hold all N(N-1)/2 pairs", who);
+	int rc = mb_store_build_transposed(ctx);
+	if (rc != MB200_OK)
+		return rc;
+	if (ctx->tr_values_stale)
+		{
+		rc = mb_store_refresh_transposed(ctx);
+		if (rc != MB200_OK)
+			return rc;
+		ctx->tr_values_stale = false;
+		}
+	return MB200_OK;
 	}
 
 extern "C" {
@@ -409,45 +713,69 @@ int mb200_align_pairs(mb200_ctx *ctx, uint32_t n, const uint32_t *store_pairs, c
 	cudaStream_t st = ctx->stream;
 	const uint32_t np = (uint32_t) ctx->h_px.size();
 	std::vector<AlnProblem> probs(n);
-	uint64_t tb_total = 0, path_total = path_off[n];
-	uint32_t lymax = 0;
+	std::vector<DensifyJob> jobs(n);
+	uint64_t dense_total = 0, tb_total = 0, edge_total = 0;
+	const uint64_t path_total = path_off[n];
+	uint32_t lxmax = 0;
 	for (uint32_t k = 0; k < n; ++k)
 		{
 		const uint32_t sp = store_pairs[k];
 		if (sp >= np)
 			return mb_fail(ctx, MB200_EINVAL, "store pair %u out of range", sp);
 		const uint32_t LX = ctx->h_len[ctx->h_px[sp]], LY = ctx->h_len[ctx->h_py[sp]];
-		tb_total += (uint64_t)(LX + 1)*(LY + 1);
-		lymax = std::max(lymax, LY);
+		if (path_off[k + 1] < path_off[k] + LX + LY + 1)
+			return mb_fail(ctx, MB200_EINVAL, "path_off[%u..%u] leaves less than LX+LY+1 bytes", k, k + 1);
+		const uint32_t ld = (LY + AW_C - 1)/AW_C*AW_C;
+		const uint32_t nstrips = (LY + AW_W - 1)/AW_W;
+		dense_total += al256((uint64_t) LX*ld*4);
+		tb_total += al256((uint64_t) LX*nstrips*32*4);
+		edge_total += al256(2*((uint64_t) LX + 1)*4);
+		lxmax = std::max(lxmax, LX);
 		}
-	ENSURE(ctx->d_tmp, tb_total + 16);
-	ENSURE(ctx->d_tmp2, path_total + n*sizeof(float) + n*sizeof(AlnProblem) + 64);
-	char *d_paths = (char *) ctx->d_tmp2.p;
-	float *d_scores = (float *)(d_paths + ((path_total + 15)/16)*16);
-	AlnProblem *d_probs = (AlnProblem *)(d_scores + ((n + 3)/4)*4);
-	uint64_t tboff = 0;
+	const size_t need = dense_total + tb_total + edge_total + al256(path_total + 16) + al256(n*sizeof(float))
+	  + al256(n*sizeof(AlnProblem)) + al256(n*sizeof(DensifyJob));
+	ENSURE(ctx->d_join, need);
+	char *p = (char *) ctx->d_join.p;
+	char *d_dense = p;               p += dense_total;
+	char *d_tb = p;                  p += tb_total;
+	char *d_edge = p;                p += edge_total;
+	char *d_paths = p;               p += al256(path_total + 16);
+	float *d_scores = (float *) p;   p += al256(n*sizeof(float));
+	AlnProblem *d_probs = (AlnProblem *) p;   p += al256(n*sizeof(AlnProblem));
+	DensifyJob *d_jobs = (DensifyJob *) p;
+	uint64_t od = 0, ot = 0, oe = 0;
 	for (uint32_t k = 0; k < n; ++k)
 		{
 		const uint32_t sp = store_pairs[k];
-		AlnProblem &p = probs[k];
-		p.LX = ctx->h_len[ctx->h_px[sp]];
-		p.LY = ctx->h_len[ctx->h_py[sp]];
-		p.dense = nullptr;
-		p.rowoff = (const uint32_t *) ctx->d_rowoff.p + ctx->h_rowbase[sp];
-		p.entries = (const mb200_entry *) ctx->d_entries.p + ctx->h_entbase[sp];
-		p.tb = (char *) ctx->d_tmp.p + tboff;
-		p.path = d_paths + path_off[k];
-		p.score = d_scores + k;
-		tboff += (uint64_t)(p.LX + 1)*(p.LY + 1);
+		const uint32_t LX = ctx->h_len[ctx->h_px[sp]], LY = ctx->h_len[ctx->h_py[sp]];
+		const uint32_t ld = (LY + AW_C - 1)/AW_C*AW_C;
+		const uint32_t nstrips = (LY + AW_W - 1)/AW_W;
+		AlnProblem &q = probs[k];
+		q.LX = LX; q.LY = LY; q.ld = ld;
+		q.dense = (const float *)(d_dense + od);
+		q.tb = (uint32_t *)(d_tb + ot);
+		q.edge = (float *)(d_edge + oe);
+		q.path = d_paths + path_off[k];
+		q.score = d_scores + k;
+		q.plen = nullptr;
+		DensifyJob &j = jobs[k];
+		j.rowoff = (const uint32_t *) ctx->d_rowoff.p + ctx->h_rowbase[sp];
+		j.entries = (const mb200_entry *) ctx->d_entries.p + ctx->h_entbase[sp];
+		j.dense = (float *)(d_dense + od);
+		j.LX = LX; j.ld = ld;
+		od += al256((uint64_t) LX*ld*4);
+		ot += al256((uint64_t) LX*nstrips*32*4);
+		oe += al256(2*((uint64_t) LX + 1)*4);
 		}
+	CU(cudaMemsetAsync(d_dense, 0, dense_total, st));
 	CU(cudaMemcpyAsync(d_probs, probs.data(), n*sizeof(AlnProblem), cudaMemcpyHostToDevice, st));
-	const size_t smem = 2*(size_t)(lymax + 1)*sizeof(float);
-	if (smem > 200*1024)
-		return mb_fail(ctx, MB200_EOVERFLOW, "sequence of length %u too long for the decoding kernel", lymax);
-	CU(cudaFuncSetAttribute(k_alnflat, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-	k_alnflat<<<n, ALN_THREADS, smem, st>>>(d_probs);
+	CU(cudaMemcpyAsync(d_jobs, jobs.data(), n*sizeof(DensifyJob), cudaMemcpyHostToDevice, st));
+	const uint64_t warps = (uint64_t) n*lxmax;
+	k_densify<<<(uint32_t)((warps*32 + 255)/256), 256, 0, st>>>(d_jobs, n, lxmax);
 	CU(cudaGetLastError());
-	ctx->stats.kernel_launches++;
+	k_aln_wave<false><<<n, 32, 0, st>>>(d_probs);
+	CU(cudaGetLastError());
+	ctx->stats.kernel_launches += 2;
 	CU(cudaMemcpyAsync(paths_out, d_paths, path_total, cudaMemcpyDeviceToHost, st));
 	CU(cudaMemcpyAsync(scores_out, d_scores, n*sizeof(float), cudaMemcpyDeviceToHost, st));
 	CU(cudaStreamSynchronize(st));
@@ -461,37 +789,23 @@ int mb200_align_groups(mb200_ctx *ctx, uint32_t na, const uint32_t *ids_a, const
 	{
 	if (!ctx || na == 0 || nb == 0 || !ids_a || !ids_b || !pos2col_a || !pos2col_b || !path_out || cols_a == 0 || cols_b == 0)
 		return mb_fail(ctx, MB200_EINVAL, "mb200_align_groups: bad argument");
-	if (!ctx->store_valid || !ctx->store_allpairs)
-		return mb_fail(ctx, MB200_EINVAL, "mb200_align_groups: the store must hold all N(N-1)/2 pairs");
 	cudaSetDevice(ctx->device);
 	cudaStream_t st = ctx->stream;
-	static bool trace_init = false;
-	if (!trace_init)
-		{
-		trace_init = true;
-		g_trace = getenv("MB200_TRACE") != nullptr;
-		if (g_trace)
-			atexit(trace_report);
-		}
-	int rc = mb_store_build_transposed(ctx);
+	trace_init();
+	int rc = need_store_for_joins(ctx, "mb200_align_groups");
 	if (rc != MB200_OK)
 		return rc;
 	double tmark = now_s();
 	++g_calls;
-	if (ctx->tr_values_stale)
-		{
-		rc = mb_store_refresh_transposed(ctx);
-		if (rc != MB200_OK)
-			return rc;
-		ctx->tr_values_stale = false;
-		}
-	// host-side index maps (tiny): col->pos for A, concatenated pos->col for B
+	// host-side index maps (tiny): col->pos for A, concatenated pos->col for B; validated here
+	std::vector<uint8_t> member(ctx->nseq, 0);
 	std::vector<int32_t> c2p((size_t) na*cols_a, -1);
 	uint64_t off = 0;
 	for (uint32_t s = 0; s < na; ++s)
 		{
-		if (ids_a[s] >= ctx->nseq)
-			return mb_fail(ctx, MB200_EINVAL, "group A sequence id out of range");
+		if (ids_a[s] >= ctx->nseq || member[ids_a[s]])
+			return mb_fail(ctx, MB200_EINVAL, "group A sequence id out of range or repeated");
+		member[ids_a[s]] = 1;
 		const uint32_t L = ctx->h_len[ids_a[s]];
 		for (uint32_t i = 0; i < L; ++i)
 			{
@@ -506,98 +820,204 @@ int mb200_align_groups(mb200_ctx *ctx, uint32_t na, const uint32_t *ids_a, const
 	uint64_t btot = 0;
 	for (uint32_t t = 0; t < nb; ++t)
 		{
-		if (ids_b[t] >= ctx->nseq)
-			return mb_fail(ctx, MB200_EINVAL, "group B sequence id out of range");
+		if (ids_b[t] >= ctx->nseq || member[ids_b[t]])
+			return mb_fail(ctx, MB200_EINVAL, "group B sequence id out of range, repeated, or also in group A "
+			  "(the reference asserts SMI_1 != SMI_2, buildpostflat.cpp:49)");
+		member[ids_b[t]] = 1;
 		boff[t] = btot;
-		btot += ctx->h_len[ids_b[t]];
+		const uint32_t L = ctx->h_len[ids_b[t]];
+		for (uint32_t i = 0; i < L; ++i)
+			if (pos2col_b[btot + i] >= cols_b)
+				return mb_fail(ctx, MB200_EINVAL, "group B pos2col out of range");
+		btot += L;
 		}
-	const size_t post_bytes = (size_t) cols_a*cols_b*sizeof(float);
-	const size_t tb_bytes = (size_t)(cols_a + 1)*(cols_b + 1);
-	const size_t path_bytes = (size_t) cols_a + cols_b + 16;
-	auto al16 = [](size_t b) { return (b + 15)/16*16; };
-	const size_t need = al16(post_bytes) + al16(tb_bytes) + al16(path_bytes) + 16 + al16(sizeof(AlnProblem))
-	  + al16(c2p.size()*4) + al16(btot*4) + al16(nb*8) + al16(na*4) + al16(nb*4) + 64;
-	ENSURE(ctx->d_tmp, need);
-	char *base = (char *) ctx->d_tmp.p;          // cudaMalloc base is 256-byte aligned; every slice 16-byte aligned
-	float *d_post = (float *) base;                  base += al16(post_bytes);
-	char *d_tb = base;                               base += al16(tb_bytes);
-	char *d_path = base;                             base += al16(path_bytes);
-	float *d_score = (float *) base;                 base += 16;
-	AlnProblem *d_prob = (AlnProblem *) base;        base += al16(sizeof(AlnProblem));
-	int32_t *d_c2p = (int32_t *) base;               base += al16(c2p.size()*4);
-	uint32_t *d_p2cb = (uint32_t *) base;            base += al16(btot*4);
-	uint64_t *d_boff = (uint64_t *) base;            base += al16(nb*8);
-	uint32_t *d_ida = (uint32_t *) base;             base += al16(na*4);
-	uint32_t *d_idb = (uint32_t *) base;
-	TRACE_MARK(0);
-	CU(cudaMemsetAsync(d_post, 0, post_bytes, st));
+	const size_t maps = al256(c2p.size()*4) + al256(btot*4) + al256(nb*8) + al256(na*4) + al256(nb*4);
+	const size_t jsz = join_scratch_bytes(cols_a, cols_b);
+	ENSURE(ctx->d_join, maps + jsz);
+	char *base = (char *) ctx->d_join.p;
+	int32_t *d_c2p = (int32_t *) base;               base += al256(c2p.size()*4);
+	uint32_t *d_p2cb = (uint32_t *) base;            base += al256(btot*4);
+	uint64_t *d_boff = (uint64_t *) base;            base += al256(nb*8);
+	uint32_t *d_ida = (uint32_t *) base;             base += al256(na*4);
+	uint32_t *d_idb = (uint32_t *) base;             base += al256(nb*4);
+	TRACE_MARK(5);
 	CU(cudaMemcpyAsync(d_c2p, c2p.data(), c2p.size()*4, cudaMemcpyHostToDevice, st));
 	CU(cudaMemcpyAsync(d_p2cb, pos2col_b, btot*4, cudaMemcpyHostToDevice, st));
 	CU(cudaMemcpyAsync(d_boff, boff.data(), nb*8, cudaMemcpyHostToDevice, st));
 	CU(cudaMemcpyAsync(d_ida, ids_a, na*4, cudaMemcpyHostToDevice, st));
 	CU(cudaMemcpyAsync(d_idb, ids_b, nb*4, cudaMemcpyHostToDevice, st));
 	ctx->stats.h2d_bytes += c2p.size()*4 + btot*4 + nb*8 + (na + nb)*4;
-	BuildPostParams P;
-	P.n = ctx->nseq; P.na = na; P.nb = nb; P.cols_a = cols_a; P.cols_b = cols_b;
-	P.ids_a = d_ida; P.ids_b = d_idb; P.col2pos_a = d_c2p; P.p2c_b = d_p2cb; P.p2c_b_off = d_boff;
-	P.rowbase = (const uint64_t *) ctx->d_rowbase.p; P.rowoff = (const uint32_t *) ctx->d_rowoff.p;
-	P.entries = (const mb200_entry *) ctx->d_entries.p;
-	P.trbase = (const uint64_t *) ctx->d_tr_rowbase.p; P.troff = (const uint32_t *) ctx->d_tr_rowoff.p;
-	P.trentries = (const mb200_entry *) ctx->d_tr_entries.p;
-	P.entbase = (const uint64_t *) ctx->d_entbase.p;
-	P.post = d_post;
-	TRACE_MARK(1);
-	const size_t acc_smem = (((size_t) BP_WARPS*cols_b*sizeof(float) + 15) & ~(size_t) 15) + (size_t) BP_WARPS*32*BP_W*sizeof(uint2);
-	if (acc_smem <= 160*1024)
-		{
-		// batches of sequences of A sized so that the staging area stays below ~512 MB
-		const uint64_t per_s = (uint64_t) cols_a*nb*(BP_W*sizeof(uint2) + 1);
-		uint32_t sb = (uint32_t) std::max<uint64_t>(1, std::min<uint64_t>(na, (512ull << 20)/std::max<uint64_t>(per_s, 1)));
-		ENSURE(ctx->d_tmp2, (uint64_t) cols_a*sb*nb*BP_W*sizeof(uint2) + (uint64_t) cols_a*sb*nb + 64);
-		BpStage G;
-		G.slots = (uint2 *) ctx->d_tmp2.p;
-		G.cnt = (uint8_t *)(G.slots + (uint64_t) cols_a*sb*nb*BP_W);
-		CU(cudaFuncSetAttribute(k_bp_apply, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) acc_smem));
-		for (uint32_t s_lo = 0; s_lo < na; s_lo += sb)
-			{
-			G.s_lo = s_lo;
-			G.s_n = std::min(sb, na - s_lo);
-			const uint64_t total = (uint64_t) cols_a*G.s_n*nb;
-			const uint32_t gblocks = (uint32_t) std::min<uint64_t>((total + 255)/256, (uint64_t) ctx->prop.multiProcessorCount*32);
-			k_bp_gather<<<gblocks, 256, 0, st>>>(P, G);
-			TRACE_MARK(2);
-			k_bp_apply<<<(cols_a + BP_WARPS - 1)/BP_WARPS, 32*BP_WARPS, acc_smem, st>>>(P, G);
-			TRACE_MARK(3);
-			ctx->stats.kernel_launches += 2;
-			}
-		}
-	else
-		{
-		// very wide alignments: row accumulators stay in global memory
-		const uint32_t groups_per_block = 128/8;
-		k_buildpost<<<(cols_a + groups_per_block - 1)/groups_per_block, 128, 0, st>>>(P);
-		}
-	CU(cudaGetLastError());
-	AlnProblem pr;
-	pr.LX = cols_a; pr.LY = cols_b; pr.dense = d_post; pr.rowoff = nullptr; pr.entries = nullptr;
-	pr.tb = d_tb; pr.path = d_path; pr.score = d_score;
-	CU(cudaMemcpyAsync(d_prob, &pr, sizeof pr, cudaMemcpyHostToDevice, st));
-	const size_t smem = 2*(size_t)(cols_b + 1)*sizeof(float);
-	if (smem > 200*1024)
-		return mb_fail(ctx, MB200_EOVERFLOW, "alignment with %u columns too wide for the decoding kernel", cols_b);
-	CU(cudaFuncSetAttribute(k_alnflat, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-	k_alnflat<<<1, ALN_THREADS, smem, st>>>(d_prob);
-	CU(cudaGetLastError());
-	ctx->stats.kernel_launches += 2;
-	TRACE_MARK(4);
-	CU(cudaMemcpyAsync(path_out, d_path, cols_a + cols_b + 1, cudaMemcpyDeviceToHost, st));
+	TRACE_MARK(0);
+	JoinBufs B;
+	rc = join_core(ctx, na, nb, d_ida, d_idb, d_c2p, d_p2cb, d_boff, cols_a, cols_b, base, jsz, B, tmark);
+	if (rc != MB200_OK)
+		return rc;
+	CU(cudaMemcpyAsync(path_out, B.path, cols_a + cols_b + 1, cudaMemcpyDeviceToHost, st));
 	if (score_out)
-		CU(cudaMemcpyAsync(score_out, d_score, sizeof(float), cudaMemcpyDeviceToHost, st));
+		CU(cudaMemcpyAsync(score_out, B.score, sizeof(float), cudaMemcpyDeviceToHost, st));
 	if (post_out)
-		CU(cudaMemcpyAsync(post_out, d_post, post_bytes, cudaMemcpyDeviceToHost, st));
+		CU(cudaMemcpy2DAsync(post_out, (size_t) cols_b*sizeof(float), B.post, (size_t) B.ld*sizeof(float),
+		  (size_t) cols_b*sizeof(float), cols_a, cudaMemcpyDeviceToHost, st));
 	CU(cudaStreamSynchronize(st));
 	TRACE_MARK(5);
-	ctx->stats.d2h_bytes += cols_a + cols_b + 1 + 4 + (post_out ? post_bytes : 0);
+	ctx->stats.d2h_bytes += cols_a + cols_b + 1 + 4 + (post_out ? (size_t) cols_a*cols_b*4 : 0);
+	return MB200_OK;
+	}
+
+// ---------------------------------------------------------------------------------------------
+// device-resident MSAs
+int mb200_msa_reset(mb200_ctx *ctx)
+	{
+	if (!ctx || ctx->nseq == 0)
+		return mb_fail(ctx, MB200_EINVAL, "mb200_msa_reset: call mb200_set_seqs first");
+	cudaSetDevice(ctx->device);
+	const uint64_t total = ctx->h_off[ctx->nseq];
+	ENSURE(ctx->d_p2c, total*sizeof(uint32_t) + 16);
+	k_msa_identity<<<ctx->prop.multiProcessorCount*4, 256, 0, ctx->stream>>>(total, (const uint64_t *) ctx->d_seqoff.p,
+	  ctx->nseq, (uint32_t *) ctx->d_p2c.p);
+	CU(cudaGetLastError());
+	ctx->stats.kernel_launches++;
+	CU(cudaStreamSynchronize(ctx->stream));
+	ctx->h_msa_cols.assign(ctx->h_len.begin(), ctx->h_len.end());     // every sequence alone (progalnflat.cpp:79-85)
+	ctx->msa_valid = true;
+	return MB200_OK;
+	}
+
+int mb200_msa_join(mb200_ctx *ctx, uint32_t na, const uint32_t *ids_a, uint32_t nb, const uint32_t *ids_b,
+  uint32_t *cols_out, float *score_out, char *path_out, uint32_t path_cap)
+	{
+	if (!ctx || na == 0 || nb == 0 || !ids_a || !ids_b)
+		return mb_fail(ctx, MB200_EINVAL, "mb200_msa_join: bad argument");
+	if (!ctx->msa_valid)
+		return mb_fail(ctx, MB200_EINVAL, "mb200_msa_join: call mb200_msa_reset first");
+	cudaSetDevice(ctx->device);
+	cudaStream_t st = ctx->stream;
+	trace_init();
+	int rc = need_store_for_joins(ctx, "mb200_msa_join");
+	if (rc != MB200_OK)
+		return rc;
+	double tmark = now_s();
+	++g_calls;
+	// members: every id once; all of A in one MSA (same column count), all of B in one MSA
+	std::vector<uint8_t> member(ctx->nseq, 0);
+	std::vector<uint32_t> ids(na + nb);
+	std::vector<uint64_t> boff(nb);
+	uint32_t lmax = 0;
+	uint64_t btot = 0;
+	for (uint32_t m = 0; m < na + nb; ++m)
+		{
+		const uint32_t s = m < na ? ids_a[m] : ids_b[m - na];
+		if (s >= ctx->nseq || member[s])
+			return mb_fail(ctx, MB200_EINVAL, "mb200_msa_join: sequence id %u out of range or listed twice", s);
+		member[s] = 1;
+		ids[m] = s;
+		lmax = std::max(lmax, ctx->h_len[s]);
+		if (m >= na)
+			{
+			boff[m - na] = btot;
+			btot += ctx->h_len[s];
+			}
+		}
+	const uint32_t old_a = ctx->h_msa_cols[ids_a[0]], old_b = ctx->h_msa_cols[ids_b[0]];
+	for (uint32_t m = 0; m < na; ++m)
+		if (ctx->h_msa_cols[ids_a[m]] != old_a)
+			return mb_fail(ctx, MB200_EINVAL, "mb200_msa_join: group A members are not in one MSA");
+	for (uint32_t m = 0; m < nb; ++m)
+		if (ctx->h_msa_cols[ids_b[m]] != old_b)
+			return mb_fail(ctx, MB200_EINVAL, "mb200_msa_join: group B members are not in one MSA");
+	const uint32_t cap = std::max(old_a, old_b);
+	// fixed part of the scratch: ids, boff, mark/remap [2][cap], map [2][cap], dims
+	const size_t fixed = al256((na + nb)*4) + al256(nb*8) + al256(2*(size_t) cap*4) + al256(2*(size_t) cap*4) + 256;
+	// upper bounds for the projected sizes are the old sizes
+	const size_t mapsz = al256((size_t) na*old_a*4) + al256(btot*4);
+	const size_t jsz = join_scratch_bytes(old_a, old_b);
+	ENSURE(ctx->d_join, fixed + mapsz + jsz);
+	char *base = (char *) ctx->d_join.p;
+	uint32_t *d_ids = (uint32_t *) base;             base += al256((na + nb)*4);
+	uint64_t *d_boff = (uint64_t *) base;            base += al256(nb*8);
+	uint32_t *d_mark = (uint32_t *) base;            base += al256(2*(size_t) cap*4);
+	uint32_t *d_map = (uint32_t *) base;             base += al256(2*(size_t) cap*4);
+	uint32_t *d_dims = (uint32_t *) base;            base += 256;
+	int32_t *d_c2p = (int32_t *) base;               base += al256((size_t) na*old_a*4);
+	uint32_t *d_p2cb = (uint32_t *) base;            base += al256(btot*4);
+	TRACE_MARK(5);
+	CU(cudaMemcpyAsync(d_ids, ids.data(), (na + nb)*4, cudaMemcpyHostToDevice, st));
+	CU(cudaMemcpyAsync(d_boff, boff.data(), nb*8, cudaMemcpyHostToDevice, st));
+	CU(cudaMemsetAsync(d_mark, 0, 2*(size_t) cap*4, st));
+	ctx->stats.h2d_bytes += (na + nb)*4 + nb*8;
+	MsaJob J;
+	memset(&J, 0, sizeof J);
+	J.na = na; J.nb = nb; J.ids = d_ids;
+	J.seqoff = (const uint64_t *) ctx->d_seqoff.p; J.seqlen = (const uint32_t *) ctx->d_seqlen.p;
+	J.p2c = (uint32_t *) ctx->d_p2c.p;
+	J.mark = d_mark; J.cap = cap; J.old_cols_a = old_a; J.old_cols_b = old_b; J.dims = d_dims;
+	J.map = d_map;
+	const dim3 mgrid((lmax + 255)/256, na + nb);
+	k_msa_mark<<<mgrid, 256, 0, st>>>(J);
+	k_msa_remap<<<2, 1024, 0, st>>>(J);
+	CU(cudaGetLastError());
+	CU(cudaMemcpyAsync(ctx->h_pinned, d_dims, 8, cudaMemcpyDeviceToHost, st));
+	CU(cudaStreamSynchronize(st));
+	const uint32_t cols_a = ctx->h_pinned[0], cols_b = ctx->h_pinned[1];
+	if (cols_a == 0 || cols_b == 0 || cols_a > old_a || cols_b > old_b)
+		return mb_fail(ctx, MB200_EINVAL, "mb200_msa_join: projection gave %u x %u columns", cols_a, cols_b);
+	J.c2p_a = d_c2p; J.cols_a = cols_a; J.p2c_b = d_p2cb; J.boff = d_boff;
+	CU(cudaMemsetAsync(d_c2p, 0xff, (size_t) na*cols_a*4, st));
+	k_msa_maps<<<mgrid, 256, 0, st>>>(J);
+	CU(cudaGetLastError());
+	ctx->stats.kernel_launches += 3;
+	TRACE_MARK(0);
+	JoinBufs B;
+	rc = join_core(ctx, na, nb, d_ids, d_ids + na, d_c2p, d_p2cb, d_boff, cols_a, cols_b, base, jsz, B, tmark);
+	if (rc != MB200_OK)
+		return rc;
+	J.path = B.path; J.plen = B.plen;
+	k_msa_pathmap<<<1, 1024, 0, st>>>(J);
+	k_msa_update<<<mgrid, 256, 0, st>>>(J);
+	CU(cudaGetLastError());
+	ctx->stats.kernel_launches += 2;
+	CU(cudaMemcpyAsync(ctx->h_pinned + 2, B.plen, 4, cudaMemcpyDeviceToHost, st));
+	CU(cudaMemcpyAsync(ctx->h_pinned + 3, B.score, 4, cudaMemcpyDeviceToHost, st));
+	if (path_out)
+		{
+		if (path_cap < cols_a + cols_b + 1)
+			return mb_fail(ctx, MB200_EINVAL, "mb200_msa_join: path buffer of %u bytes, need %u", path_cap, cols_a + cols_b + 1);
+		CU(cudaMemcpyAsync(path_out, B.path, cols_a + cols_b + 1, cudaMemcpyDeviceToHost, st));
+		}
+	CU(cudaStreamSynchronize(st));
+	TRACE_MARK(4);
+	const uint32_t newcols = ctx->h_pinned[2];
+	for (uint32_t m = 0; m < na + nb; ++m)
+		ctx->h_msa_cols[ids[m]] = newcols;
+	if (cols_out)
+		*cols_out = newcols;
+	if (score_out)
+		memcpy(score_out, ctx->h_pinned + 3, 4);
+	ctx->stats.d2h_bytes += 16 + (path_out ? cols_a + cols_b + 1 : 0);
+	return MB200_OK;
+	}
+
+int mb200_msa_export(mb200_ctx *ctx, uint32_t n, const uint32_t *ids, uint32_t *pos2col_out, uint32_t *cols_out)
+	{
+	if (!ctx || n == 0 || !ids || !pos2col_out)
+		return mb_fail(ctx, MB200_EINVAL, "mb200_msa_export: bad argument");
+	if (!ctx->msa_valid)
+		return mb_fail(ctx, MB200_EINVAL, "mb200_msa_export: call mb200_msa_reset first");
+	cudaSetDevice(ctx->device);
+	uint64_t off = 0;
+	for (uint32_t k = 0; k < n; ++k)
+		{
+		const uint32_t s = ids[k];
+		if (s >= ctx->nseq)
+			return mb_fail(ctx, MB200_EINVAL, "mb200_msa_export: sequence id out of range");
+		CU(cudaMemcpyAsync(pos2col_out + off, (const uint32_t *) ctx->d_p2c.p + ctx->h_off[s], ctx->h_len[s]*sizeof(uint32_t),
+		  cudaMemcpyDeviceToHost, ctx->stream));
+		off += ctx->h_len[s];
+		if (cols_out)
+			cols_out[k] = ctx->h_msa_cols[s];
+		}
+	CU(cudaStreamSynchronize(ctx->stream));
+	ctx->stats.d2h_bytes += off*4;
 	return MB200_OK;
 	}
 

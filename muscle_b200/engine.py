@@ -22,7 +22,7 @@ EXPORTS = [
 	"mb200_store_exchange_begin", "mb200_store_exchange_commit", "mb200_store_entries_ptr", "mb200_store_values_changed",
 	"mb200_group_create", "mb200_group_destroy", "mb200_group_last_error", "mb200_group_size", "mb200_group_ctx",
 	"mb200_group_set_hmm", "mb200_group_set_seqs", "mb200_group_posteriors_allpairs", "mb200_group_consistency_iter",
-	"mb200_group_get_stats",
+	"mb200_group_get_stats", "mb200_msa_reset", "mb200_msa_join", "mb200_msa_export",
 ]
 
 
@@ -276,6 +276,36 @@ class Engine:
 		self._ck(self.lib.mb200_align_groups(self.h, C.c_uint32(len(ia)), _ptr(ia), _ptr(pa), C.c_uint32(cols_a),
 		  C.c_uint32(len(ib)), _ptr(ib), _ptr(pb), C.c_uint32(cols_b), path, C.byref(score), _ptr(post)))
 		return score.value, path.value.decode(), post
+
+	# ---- device-resident MSAs
+	def msa_reset(self):
+		self._ck(self.lib.mb200_msa_reset(self.h))
+
+	def msa_join(self, ids_a, ids_b, want_path=False):
+		"""-> (columns of the joined MSA, DP score, path or None)"""
+		ia = np.ascontiguousarray(ids_a, np.uint32)
+		ib = np.ascontiguousarray(ids_b, np.uint32)
+		cols = C.c_uint32()
+		score = C.c_float()
+		cap = int(sum(int(self.lens[i]) for i in list(ia) + list(ib))) + 2 if want_path else 0
+		path = C.create_string_buffer(cap) if want_path else None
+		self._ck(self.lib.mb200_msa_join(self.h, C.c_uint32(len(ia)), _ptr(ia), C.c_uint32(len(ib)), _ptr(ib),
+		  C.byref(cols), C.byref(score), path, C.c_uint32(cap)))
+		return cols.value, score.value, (path.value.decode() if want_path else None)
+
+	def msa_export(self, ids):
+		"""-> (list of pos->col arrays, list of column counts)"""
+		ii = np.ascontiguousarray(ids, np.uint32)
+		tot = int(sum(int(self.lens[i]) for i in ii))
+		buf = np.empty(tot, np.uint32)
+		cols = np.empty(len(ii), np.uint32)
+		self._ck(self.lib.mb200_msa_export(self.h, C.c_uint32(len(ii)), _ptr(ii), _ptr(buf), _ptr(cols)))
+		out, o = [], 0
+		for i in ii:
+			L = int(self.lens[i])
+			out.append(buf[o:o + L].copy())
+			o += L
+		return out, cols
 
 	def stats(self):
 		s = Stats()

@@ -47,6 +47,33 @@ def super5():
 	subprocess.run([CLI, "-super5", fa, "-output", os.path.join(OUT, "super5_150.ref.afa"), "-quiet", "-threads", "1"], check=True)
 
 
+def profalign():
+	"""-profalign golden: the two halves of fam12's reference MSA (projected), re-joined by the reference"""
+	def read(path):
+		rows, name = [], None
+		for line in open(path):
+			line = line.strip()
+			if line.startswith(">"):
+				name = line[1:]
+				rows.append([name, ""])
+			elif name is not None:
+				rows[-1][1] += line
+		return rows
+
+	def proj(rs):
+		cols = len(rs[0][1])
+		keep = [c for c in range(cols) if any(r[1][c] != "-" for r in rs)]
+		return [(n, "".join(q[c] for c in keep)) for n, q in rs]
+	rows = read(os.path.join(OUT, "fam12.ref.afa"))
+	for nm, rs in (("profalign_a.afa", proj(rows[:5])), ("profalign_b.afa", proj(rows[5:]))):
+		with open(os.path.join(OUT, nm), "w") as f:
+			for n, q in rs:
+				f.write(">%s\n%s\n" % (n, q))
+	subprocess.run([CLI, "-profalign", os.path.join(OUT, "profalign_a.afa"), "-input2", os.path.join(OUT, "profalign_b.afa"),
+	  "-output", os.path.join(OUT, "profalign.ref.afa"), "-quiet"], check=True)
+
+
 if __name__ == "__main__":
 	super5()
 	main()
+	profalign()

@@ -85,3 +85,36 @@ def test_super5_cli_matches_reference_msa(tmp_path):
 	a, b = pair_set(got), pair_set(want)
 	q = len(a & b)/max(1, len(b))
 	assert q >= 0.98, "super5 MSA differs from the reference: shared aligned pairs %.4f" % q
+
+
+def test_profalign_cli_matches_reference_msa(tmp_path):
+	"""`-profalign` never calls CalcPosteriors: it calls MPCFlat::CalcPosterior per cross pair and then
+	AlignAlns (profalign.cpp:28-54).  The binding defers the per-pair calls and runs one device batch."""
+	if not os.path.exists(CLI):
+		pytest.skip("integration/_build/muscle_b200 not built (needs /root/reference at build time)")
+	out = tmp_path / "profalign.afa"
+	r = subprocess.run([CLI, "-profalign", os.path.join(E2E, "profalign_a.afa"), "-input2", os.path.join(E2E, "profalign_b.afa"),
+	  "-output", str(out), "-quiet"], capture_output=True, text=True, timeout=600)
+	assert r.returncode == 0, r.stderr[-2000:]
+	assert read_afa(out) == read_afa(os.path.join(E2E, "profalign.ref.afa"))
+
+
+def test_align_cli_c2_matches_reference_msa(tmp_path):
+	"""BASELINE.json config 2 (256 proteins, mean length 250) end to end: posteriors, 2 consistency
+	iterations, 255 device joins, 100 refinement joins -- byte-identical to the CPU reference's MSA
+	(tests/golden/e2e/c2.ref.afa, ~35 CPU-minutes on 6 threads to produce)."""
+	if not os.path.exists(CLI):
+		pytest.skip("integration/_build/muscle_b200 not built (needs /root/reference at build time)")
+	ref = os.path.join(E2E, "c2.ref.afa")
+	if not os.path.exists(ref):
+		pytest.skip("c2 golden not generated")
+	from muscle_b200 import synth
+	fa = tmp_path / "c2.fa"
+	with open(fa, "w") as f:
+		for i, q in enumerate(synth.make_config("C2")):
+			f.write(">s%d\n%s\n" % (i, q))
+	out = tmp_path / "c2.afa"
+	r = subprocess.run([CLI, "-align", str(fa), "-output", str(out), "-quiet"], capture_output=True, text=True, timeout=900)
+	assert r.returncode == 0, r.stderr[-2000:]
+	got, want = read_afa(out), read_afa(ref)
+	assert got == want
