@@ -8,20 +8,21 @@
 // MultiSequence::Project (project.cpp:16-69) on position->column maps, i.e. the data path of
 // MPCFlat::ProgAln (progalnflat.cpp:41-71) and MPCFlat::RefineIter (refineflat.cpp:4-31).
 //
-// Decoding DP (k_aln_wave).  One warp per problem; lane l owns 16 consecutive columns of a
-// 512-column strip and the rows are swept as an anti-diagonal wavefront (lane l is on row t-l at
-// step t, the left neighbour's value arrives by one shuffle), exactly the reference's recurrence
+// Decoding DP (k_aln_wave).  One CTA per problem, one warp per 512-column strip; lane l owns 16
+// consecutive columns and the rows are swept as an anti-diagonal wavefront (lane l is on row t-l at
+// step t, the left neighbour's value arrives by one shuffle, the left strip's through a shared-memory
+// ring), exactly the reference's recurrence
 //      new[j] = max3(old[j-1] + P[i][j], old[j], new[j-1])
 // evaluated with the same fp32 add and the same operands, so scores are bit-identical; the
 // traceback letter follows Best3's tie rule (B if B>=X and B>=Y; else Y if B>=X; else X if X>=Y else
 // Y) and is stored as 2 bits per cell (shared memory when it fits, else global), then walked by
-// lane 0 and reversed by the warp.  Round 1 used one CTA with 4+ barriers per row and a serial
-// traceback through global memory: 6.8 ms per 500x500 join; this is ~0.1 ms.
+// warp 0 (32 rows of traceback words cached across the lanes) and reversed.  Round 1 used one CTA
+// with 4+ barriers per row and a serial traceback through global memory.
 //
 // BuildPost.  Every cell is a sum over (s,t) in the reference's s-major/t-minor order with at most
 // one term per (s,t); the order is kept per cell, everything else is parallel.  Phase 1 (k_bp_gather,
-// one thread per (row, s, t)) does the random gathers into the store and writes each needed sparse
-// row, mapped to columns of B, into a 16-entry staging slot; phase 2 (k_bp_apply, one warp per row,
+// one thread per (residue of A's members, t)) does the random gathers into the store and writes each
+// needed sparse row, mapped to columns of B, into a 16-entry staging slot; phase 2 (k_bp_apply, one warp per row,
 // accumulator row in shared memory) streams the slots through a cp.async double buffer and applies
 // them strictly in order, the entries of one sparse row in parallel.
 #include "engine.h"
@@ -78,96 +79,145 @@ struct AlnProblem
 	uint32_t *plen;                  // may be nullptr
 	};
 
+#define AW_MAXW 16                   // warps per CTA = strips in flight
+#define AW_RING 64                   // rows of slack between neighbouring strips
+
+// One CTA per problem, one warp per 512-column strip (AW_MAXW strips in flight, wider problems in
+// several passes).  Inside a warp the rows are an anti-diagonal wavefront over the lanes; between
+// warps the same wavefront continues: strip w+1 consumes, row by row, the last column of strip w
+// through a shared-memory ring guarded by a progress counter, so a 5000 x 5000 join takes ~LX+32*strips
+// steps instead of LX*strips.
 template <bool TB_SMEM>
-__global__ void __launch_bounds__(32)
+__global__ void __launch_bounds__(32*AW_MAXW)
 k_aln_wave(const AlnProblem *probs)
 	{
 	extern __shared__ uint32_t tb_sm[];
+	__shared__ float ring[AW_MAXW][AW_RING];
+	__shared__ int prog[AW_MAXW], cons[AW_MAXW];
+	__shared__ float finalS;
 	const AlnProblem pr = probs[blockIdx.x];
-	const int lane = threadIdx.x;
+	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+	const int NW = blockDim.x >> 5;
 	const int LX = (int) pr.LX, LY = (int) pr.LY;
 	const int nstrips = (LY + AW_W - 1)/AW_W;
+	const int npass = (nstrips + NW - 1)/NW;
 	uint32_t *tb = TB_SMEM ? tb_sm : pr.tb;
-	float finalScore = 0.0f;
-	for (int strip = 0; strip < nstrips; ++strip)
+	volatile int *vprog = prog, *vcons = cons;
+	for (int pass = 0; pass < npass; ++pass)
 		{
-		const int j0 = strip*AW_W;
-		const int ncol = min(AW_W, LY - j0);
-		const int nl = (ncol + AW_C - 1)/AW_C;
-		const float *edgeIn = pr.edge + (size_t)(strip & 1)*(LX + 1);
-		float *edgeOut = pr.edge + (size_t)((strip + 1) & 1)*(LX + 1);
-		const bool hasIn = strip > 0, hasOut = strip + 1 < nstrips;
-		float old[AW_C];
-#pragma unroll
-		for (int c = 0; c < AW_C; ++c)
-			old[c] = 0.0f;                                   // row 0 (calcalnflat.cpp:15-19)
-		float outNew = 0.0f, prevRecv = 0.0f;
-		const float *src = pr.dense + j0 + lane*AW_C;
-		float4 nx0, nx1, nx2, nx3;
-		nx0 = nx1 = nx2 = nx3 = make_float4(0.f, 0.f, 0.f, 0.f);
-		if (lane == 0 && LX >= 1)
+		if (lane == 0)
 			{
-			const float4 *q = reinterpret_cast<const float4 *>(src);
-			nx0 = q[0]; nx1 = q[1]; nx2 = q[2]; nx3 = q[3];
+			prog[wid] = 0; cons[wid] = 0;
 			}
-		const int nsteps = LX + nl - 1;
-		// the lane that owns DP column LY (for the final score)
-		const int lastLane = (LY - 1 - j0)/AW_C, lastC = (LY - 1 - j0) % AW_C;
-		for (int t = 0; t < nsteps; ++t)
+		__syncthreads();
+		const int strip = pass*NW + wid;
+		if (strip < nstrips)
 			{
-			const int i = t - lane + 1;                      // 1-based row
-			float recv = __shfl_up_sync(MB_FULL, outNew, 1);
-			if (lane == 0)
-				recv = (hasIn && i >= 0 && i <= LX) ? edgeIn[i] : 0.0f;
-			const bool valid = i >= 1 && i <= LX && lane < nl;
-			float p[AW_C];
-			p[0] = nx0.x; p[1] = nx0.y; p[2] = nx0.z; p[3] = nx0.w; p[4] = nx1.x; p[5] = nx1.y; p[6] = nx1.z; p[7] = nx1.w;
-			p[8] = nx2.x; p[9] = nx2.y; p[10] = nx2.z; p[11] = nx2.w; p[12] = nx3.x; p[13] = nx3.y; p[14] = nx3.z; p[15] = nx3.w;
-			// prefetch the row this lane works on in the next step
-			if (lane < nl && i + 1 >= 1 && i + 1 <= LX)
+			const int j0 = strip*AW_W;
+			const int ncol = min(AW_W, LY - j0);
+			const int nl = (ncol + AW_C - 1)/AW_C;
+			const bool hasIn = strip > 0, hasOut = strip + 1 < nstrips;
+			const bool ringIn = hasIn && wid > 0;                    // else the previous pass left it in global memory
+			const bool ringOut = hasOut && wid + 1 < NW;
+			const float *edgeIn = pr.edge + (size_t)(pass & 1)*(LX + 1);
+			float *edgeOut = pr.edge + (size_t)((pass + 1) & 1)*(LX + 1);
+			float old[AW_C];
+#pragma unroll
+			for (int c = 0; c < AW_C; ++c)
+				old[c] = 0.0f;                                   // row 0 (calcalnflat.cpp:15-19)
+			float outNew = 0.0f, prevRecv = 0.0f;
+			const float *src = pr.dense + j0 + lane*AW_C;
+			float4 nx0, nx1, nx2, nx3;
+			nx0 = nx1 = nx2 = nx3 = make_float4(0.f, 0.f, 0.f, 0.f);
+			if (lane == 0 && LX >= 1)
 				{
-				const float4 *q = reinterpret_cast<const float4 *>(src + (size_t) i*pr.ld);
+				const float4 *q = reinterpret_cast<const float4 *>(src);
 				nx0 = q[0]; nx1 = q[1]; nx2 = q[2]; nx3 = q[3];
 				}
-			if (valid)
+			const int nsteps = LX + nl - 1;
+			// the lane that owns DP column LY (for the final score)
+			const int lastLane = (LY - 1 - j0)/AW_C, lastC = (LY - 1 - j0) % AW_C;
+			for (int t = 0; t < nsteps; ++t)
 				{
-				float Y = recv;                                // new[i][first col - 1]
-				float diag = prevRecv;                         // new[i-1][first col - 1]
-				uint32_t word = 0;
-#pragma unroll
-				for (int c = 0; c < AW_C; ++c)
+				const int i = t - lane + 1;                      // 1-based row
+				float recv = __shfl_up_sync(MB_FULL, outNew, 1);
+				if (lane == 0)
 					{
-					const float B = __fadd_rn(diag, p[c]);       // calcalnflat.cpp:31-37
-					const float X = old[c];
-					const float nw = fmaxf(fmaxf(B, X), Y);
-					const uint32_t code = (B >= X) ? ((B >= Y) ? 0u : 2u) : ((X >= Y) ? 1u : 2u);    // best3.h:5-28
-					word |= code << (2*c);
-					diag = X;
-					old[c] = nw;
-					Y = nw;
-					if (c == lastC && lane == lastLane && i == LX && strip == nstrips - 1)
-						finalScore = nw;
+					recv = 0.0f;
+					if (hasIn && i >= 1 && i <= LX)
+						{
+						if (ringIn)
+							{
+							while (vprog[wid - 1] < i)
+								;                                     // strip on the left has not produced row i yet
+							recv = ((volatile float *) ring[wid - 1])[i % AW_RING];
+							vcons[wid] = i;
+							}
+						else
+							recv = edgeIn[i];
+						}
 					}
-				outNew = Y;
-				tb[((size_t)(i - 1)*nstrips + strip)*32 + lane] = word;
-				if (hasOut && lane == 31)
-					edgeOut[i] = outNew;
+				const bool valid = i >= 1 && i <= LX && lane < nl;
+				float p[AW_C];
+				p[0] = nx0.x; p[1] = nx0.y; p[2] = nx0.z; p[3] = nx0.w; p[4] = nx1.x; p[5] = nx1.y; p[6] = nx1.z; p[7] = nx1.w;
+				p[8] = nx2.x; p[9] = nx2.y; p[10] = nx2.z; p[11] = nx2.w; p[12] = nx3.x; p[13] = nx3.y; p[14] = nx3.z; p[15] = nx3.w;
+				// prefetch the row this lane works on in the next step
+				if (lane < nl && i + 1 >= 1 && i + 1 <= LX)
+					{
+					const float4 *q = reinterpret_cast<const float4 *>(src + (size_t) i*pr.ld);
+					nx0 = q[0]; nx1 = q[1]; nx2 = q[2]; nx3 = q[3];
+					}
+				if (valid)
+					{
+					float Y = recv;                                // new[i][first col - 1]
+					float diag = prevRecv;                         // new[i-1][first col - 1]
+					uint32_t word = 0;
+#pragma unroll
+					for (int c = 0; c < AW_C; ++c)
+						{
+						const float B = __fadd_rn(diag, p[c]);       // calcalnflat.cpp:31-37
+						const float X = old[c];
+						const float nw = fmaxf(fmaxf(B, X), Y);
+						const uint32_t code = (B >= X) ? ((B >= Y) ? 0u : 2u) : ((X >= Y) ? 1u : 2u);    // best3.h:5-28
+						word |= code << (2*c);
+						diag = X;
+						old[c] = nw;
+						Y = nw;
+						if (c == lastC && lane == lastLane && i == LX && strip == nstrips - 1)
+							finalS = nw;
+						}
+					outNew = Y;
+					tb[((size_t)(i - 1)*nstrips + strip)*32 + lane] = word;
+					if (hasOut && lane == 31)
+						{
+						if (ringOut)
+							{
+							while (i > AW_RING && vcons[wid + 1] < i - AW_RING)
+								;                                     // the slot still holds an unconsumed row
+							((volatile float *) ring[wid])[i % AW_RING] = outNew;
+							__threadfence_block();
+							vprog[wid] = i;
+							}
+						else
+							edgeOut[i] = outNew;
+						}
+					}
+				prevRecv = recv;
+				__syncwarp();
 				}
-			prevRecv = recv;
 			}
-		if (hasOut && lane == 31)
-			edgeOut[0] = 0.0f;
-		__syncwarp();
+		__syncthreads();
 		}
-	finalScore = __shfl_sync(MB_FULL, finalScore, (LY - 1 - (nstrips - 1)*AW_W)/AW_C);
-	__syncwarp();
-	// traceback (tracebackflat.cpp:3-37): TB(0,j) = 'Y', TB(i,0) = 'X'
+	// traceback (tracebackflat.cpp:3-37): TB(0,j) = 'Y', TB(i,0) = 'X'.  Warp 0, all lanes in lockstep
+	// on the same (i,j); the lanes hold the traceback words of 32 consecutive rows of the current
+	// 16-column group so that a dependent load is needed only every ~16 steps.
+	if (wid != 0)
+		return;
 	uint32_t n = 0;
-	if (lane == 0)
 		{
 		int i = LX, j = LY;
-		int curRow = -1, curIdx = -1;
-		uint32_t w = 0;
+		int cbase = -1, cidx = -1;
+		uint32_t cw = 0;
 		while (i != 0 || j != 0)
 			{
 			char t;
@@ -179,25 +229,32 @@ k_aln_wave(const AlnProblem *probs)
 				{
 				const int jj = j - 1;
 				const int idx = (jj/AW_W)*32 + (jj % AW_W)/AW_C;
-				if (i != curRow || idx != curIdx)
+				int d = cbase - i;
+				if (idx != cidx || d < 0 || d >= 32)
 					{
-					w = tb[(size_t)(i - 1)*nstrips*32 + idx];
-					curRow = i; curIdx = idx;
+					cbase = i; cidx = idx; d = 0;
+					const int r = i - lane;
+					cw = r >= 1 ? tb[(size_t)(r - 1)*nstrips*32 + idx] : 0u;
 					}
+				const uint32_t w = __shfl_sync(MB_FULL, cw, d);
 				const uint32_t code = (w >> (2*(jj % AW_C))) & 3u;
 				t = code == 0 ? 'B' : (code == 1 ? 'X' : 'Y');
 				}
-			pr.path[n++] = t;
+			if (lane == 0)
+				pr.path[n] = t;
+			++n;
 			if (t == 'B') { --i; --j; }
 			else if (t == 'X') --i;
 			else --j;
 			}
-		pr.path[n] = 0;
-		*pr.score = finalScore;
-		if (pr.plen)
-			*pr.plen = n;
+		if (lane == 0)
+			{
+			pr.path[n] = 0;
+			*pr.score = finalS;
+			if (pr.plen)
+				*pr.plen = n;
+			}
 		}
-	n = __shfl_sync(MB_FULL, n, 0);
 	__syncwarp();
 	for (uint32_t a = lane; a < n/2; a += 32)
 		{
@@ -244,9 +301,12 @@ struct BuildPostParams
 
 struct BpStage
 	{
-	uint2   *slots;      // [row][s_local][t][BP_W]  (column of B, bits of P)
-	uint8_t *cnt;        // [row][s_local][t]; 255 = row longer than BP_W (applied by direct gather)
+	uint2   *slots;      // [residue of the batch][t][BP_W]  (column of B, bits of P)
+	uint8_t *cnt;        // [residue][t]; 255 = row longer than BP_W (applied by direct gather)
 	uint32_t s_lo, s_n;  // batch of sequences of A
+	const uint32_t *rb;  // [na+1] residues of A's members before member s (slots exist for residues only:
+	                     // indexing by (column, s) would stage mostly gaps -- a 1000-row MSA of 350-residue
+	                     // proteins has 7000+ columns)
 	};
 
 __device__ __forceinline__ void bp_operand(const BuildPostParams &P, uint32_t a, uint32_t b, const uint32_t *&ro,
@@ -267,36 +327,38 @@ __device__ __forceinline__ void bp_operand(const BuildPostParams &P, uint32_t a,
 __global__ void __launch_bounds__(256)
 k_bp_gather(const BuildPostParams P, const BpStage G)
 	{
-	const uint64_t total = (uint64_t) P.cols_a*G.s_n*P.nb;
+	const uint32_t r0 = G.rb[G.s_lo];
+	const uint64_t total = (uint64_t)(G.rb[G.s_lo + G.s_n] - r0)*P.nb;
 	for (uint64_t idx = blockIdx.x*(uint64_t) blockDim.x + threadIdx.x; idx < total; idx += (uint64_t) gridDim.x*blockDim.x)
 		{
 		const uint32_t t = (uint32_t)(idx % P.nb);
-		const uint64_t rs = idx/P.nb;
-		const uint32_t sl = (uint32_t)(rs % G.s_n);
-		const uint32_t row = (uint32_t)(rs/G.s_n);
-		const uint32_t s = G.s_lo + sl;
-		const int32_t pos = P.col2pos_a[(size_t) s*P.cols_a + row];
-		uint32_t n = 0;
-		if (pos >= 0)
+		const uint32_t r = r0 + (uint32_t)(idx/P.nb);
+		// member of A that owns residue r: largest s with rb[s] <= r
+		uint32_t lo = G.s_lo, hi = G.s_lo + G.s_n;
+		while (hi - lo > 1)
 			{
-			const uint32_t *ro;
-			const mb200_entry *en;
-			bp_operand(P, P.ids_a[s], P.ids_b[t], ro, en);
-			const uint32_t e0 = ro[pos];
-			n = ro[pos + 1] - e0;
-			if (n <= BP_W)
-				{
-				const uint32_t *p2c = P.p2c_b + P.p2c_b_off[t];
-				uint2 *dst = G.slots + idx*BP_W;
-				for (uint32_t k = 0; k < n; ++k)
-					{
-					const mb200_entry v = en[e0 + k];
-					dst[k] = make_uint2(p2c[v.col], __float_as_uint(v.p));
-					}
-				}
-			else
-				n = 255;
+			const uint32_t mid = (lo + hi) >> 1;
+			if (G.rb[mid] <= r) lo = mid; else hi = mid;
 			}
+		const uint32_t s = lo;
+		const uint32_t pos = r - G.rb[s];
+		const uint32_t *ro;
+		const mb200_entry *en;
+		bp_operand(P, P.ids_a[s], P.ids_b[t], ro, en);
+		const uint32_t e0 = ro[pos];
+		uint32_t n = ro[pos + 1] - e0;
+		if (n <= BP_W)
+			{
+			const uint32_t *p2c = P.p2c_b + P.p2c_b_off[t];
+			uint2 *dst = G.slots + idx*BP_W;
+			for (uint32_t k = 0; k < n; ++k)
+				{
+				const mb200_entry v = en[e0 + k];
+				dst[k] = make_uint2(p2c[v.col], __float_as_uint(v.p));
+				}
+			}
+		else
+			n = 255;
 		G.cnt[idx] = (uint8_t) n;
 		}
 	}
@@ -328,7 +390,7 @@ k_bp_apply(const BuildPostParams P, const BpStage G)
 		const int32_t pos = P.col2pos_a[(size_t) s*P.cols_a + row];
 		if (pos < 0)
 			continue;
-		const uint64_t base = ((uint64_t) row*G.s_n + sl)*P.nb;
+		const uint64_t base = (uint64_t)(G.rb[s] - G.rb[G.s_lo] + (uint32_t) pos)*P.nb;
 		// prologue: group 0 in flight
 		uint32_t cntNext = 0;
 		{
@@ -600,15 +662,15 @@ struct JoinBufs                       // carved out of ctx->d_join
 // BuildPost + decoding DP of groups whose maps are already on the device.  Leaves path / plen /
 // score on the device (JoinBufs) and does NOT synchronise.
 static int join_core(mb200_ctx *ctx, uint32_t na, uint32_t nb, const uint32_t *d_ida, const uint32_t *d_idb,
-  const int32_t *d_c2pa, const uint32_t *d_p2cb, const uint64_t *d_boff, uint32_t cols_a, uint32_t cols_b,
-  char *scratch, size_t scratch_bytes, JoinBufs &B, double &tmark)
+  const int32_t *d_c2pa, const uint32_t *d_p2cb, const uint64_t *d_boff, const uint32_t *d_rb, const std::vector<uint32_t> &h_rb,
+  uint32_t cols_a, uint32_t cols_b, char *scratch, size_t scratch_bytes, JoinBufs &B, double &tmark)
 	{
 	cudaStream_t st = ctx->stream;
 	const uint32_t ld = (cols_b + AW_C - 1)/AW_C*AW_C;
 	const uint32_t nstrips = (cols_b + AW_W - 1)/AW_W;
 	const size_t post_bytes = (size_t) cols_a*ld*sizeof(float);
 	const size_t tbw = (size_t) cols_a*nstrips*32*sizeof(uint32_t);
-	const bool tb_smem = tbw <= 200*1024;
+	const bool tb_smem = tbw <= 192*1024;
 	char *p = scratch;
 	B.post = (float *) p;            p += al256(post_bytes);
 	B.tb = (uint32_t *) p;           p += tb_smem ? 256 : al256(tbw);
@@ -635,20 +697,31 @@ static int join_core(mb200_ctx *ctx, uint32_t na, uint32_t nb, const uint32_t *d
 	const size_t acc_smem = (((size_t) BP_WARPS*cols_b*sizeof(float) + 15) & ~(size_t) 15) + (size_t) BP_WARPS*2*BP_G*BP_W*sizeof(uint2);
 	if (acc_smem > 220*1024)
 		return mb_fail(ctx, MB200_EOVERFLOW, "alignment with %u columns too wide for the BuildPost kernel", cols_b);
-	// batches of sequences of A sized so that the staging area stays below ~1 GB
-	const uint64_t per_s = (uint64_t) cols_a*nb*(BP_W*sizeof(uint2) + 1);
-	const uint32_t sb = (uint32_t) std::max<uint64_t>(1, std::min<uint64_t>(na, (1024ull << 20)/std::max<uint64_t>(per_s, 1)));
-	const uint64_t nslots = (uint64_t) cols_a*sb*nb;
-	ENSURE(ctx->d_stage, nslots*BP_W*sizeof(uint2) + nslots + 256);
+	// batches of sequences of A sized so that the staging area (one slot per residue of the batch and
+	// member of B) stays below ~2 GB
+	const uint64_t budget_slots = (2048ull << 20)/(BP_W*sizeof(uint2) + 1);
+	uint64_t max_slots = 0;
+	std::vector<uint32_t> cuts(1, 0);
+	for (uint32_t s = 0; s < na; )
+		{
+		uint32_t e = s + 1;
+		while (e < na && (uint64_t)(h_rb[e + 1] - h_rb[s])*nb <= budget_slots)
+			++e;
+		max_slots = std::max<uint64_t>(max_slots, (uint64_t)(h_rb[e] - h_rb[s])*nb);
+		cuts.push_back(e);
+		s = e;
+		}
+	ENSURE(ctx->d_stage, max_slots*BP_W*sizeof(uint2) + max_slots + 256);
 	BpStage G;
 	G.slots = (uint2 *) ctx->d_stage.p;
-	G.cnt = (uint8_t *)(G.slots + nslots*BP_W);
+	G.cnt = (uint8_t *)(G.slots + max_slots*BP_W);
+	G.rb = d_rb;
 	CU(cudaFuncSetAttribute(k_bp_apply, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) acc_smem));
-	for (uint32_t s_lo = 0; s_lo < na; s_lo += sb)
+	for (size_t b = 0; b + 1 < cuts.size(); ++b)
 		{
-		G.s_lo = s_lo;
-		G.s_n = std::min(sb, na - s_lo);
-		const uint64_t total = (uint64_t) cols_a*G.s_n*nb;
+		G.s_lo = cuts[b];
+		G.s_n = cuts[b + 1] - cuts[b];
+		const uint64_t total = (uint64_t)(h_rb[cuts[b + 1]] - h_rb[cuts[b]])*nb;
 		const uint32_t gblocks = (uint32_t) std::min<uint64_t>((total + 255)/256, (uint64_t) ctx->prop.multiProcessorCount*32);
 		k_bp_gather<<<gblocks, 256, 0, st>>>(P, G);
 		TRACE_MARK(1);
@@ -661,13 +734,14 @@ static int join_core(mb200_ctx *ctx, uint32_t na, uint32_t nb, const uint32_t *d
 	pr.LX = cols_a; pr.LY = cols_b; pr.ld = ld; pr.dense = B.post; pr.tb = B.tb; pr.edge = B.edge;
 	pr.path = B.path; pr.score = B.score; pr.plen = B.plen;
 	CU(cudaMemcpyAsync(B.prob, &pr, sizeof pr, cudaMemcpyHostToDevice, st));
+	const uint32_t nwarps = std::min<uint32_t>(AW_MAXW, nstrips);
 	if (tb_smem)
 		{
 		CU(cudaFuncSetAttribute(k_aln_wave<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) std::max<size_t>(tbw, 16)));
-		k_aln_wave<true><<<1, 32, tbw, st>>>(B.prob);
+		k_aln_wave<true><<<1, 32*nwarps, tbw, st>>>(B.prob);
 		}
 	else
-		k_aln_wave<false><<<1, 32, 0, st>>>(B.prob);
+		k_aln_wave<false><<<1, 32*nwarps, 0, st>>>(B.prob);
 	CU(cudaGetLastError());
 	ctx->stats.kernel_launches++;
 	TRACE_MARK(3);
@@ -716,7 +790,7 @@ int mb200_align_pairs(mb200_ctx *ctx, uint32_t n, const uint32_t *store_pairs, c
 	std::vector<DensifyJob> jobs(n);
 	uint64_t dense_total = 0, tb_total = 0, edge_total = 0;
 	const uint64_t path_total = path_off[n];
-	uint32_t lxmax = 0;
+	uint32_t lxmax = 0, maxstrips = 1;
 	for (uint32_t k = 0; k < n; ++k)
 		{
 		const uint32_t sp = store_pairs[k];
@@ -731,6 +805,7 @@ int mb200_align_pairs(mb200_ctx *ctx, uint32_t n, const uint32_t *store_pairs, c
 		tb_total += al256((uint64_t) LX*nstrips*32*4);
 		edge_total += al256(2*((uint64_t) LX + 1)*4);
 		lxmax = std::max(lxmax, LX);
+		maxstrips = std::max(maxstrips, nstrips);
 		}
 	const size_t need = dense_total + tb_total + edge_total + al256(path_total + 16) + al256(n*sizeof(float))
 	  + al256(n*sizeof(AlnProblem)) + al256(n*sizeof(DensifyJob));
@@ -773,7 +848,7 @@ int mb200_align_pairs(mb200_ctx *ctx, uint32_t n, const uint32_t *store_pairs, c
 	const uint64_t warps = (uint64_t) n*lxmax;
 	k_densify<<<(uint32_t)((warps*32 + 255)/256), 256, 0, st>>>(d_jobs, n, lxmax);
 	CU(cudaGetLastError());
-	k_aln_wave<false><<<n, 32, 0, st>>>(d_probs);
+	k_aln_wave<false><<<n, 32*std::min<uint32_t>(AW_MAXW, maxstrips), 0, st>>>(d_probs);
 	CU(cudaGetLastError());
 	ctx->stats.kernel_launches += 2;
 	CU(cudaMemcpyAsync(paths_out, d_paths, path_total, cudaMemcpyDeviceToHost, st));
@@ -816,6 +891,9 @@ int mb200_align_groups(mb200_ctx *ctx, uint32_t na, const uint32_t *ids_a, const
 			}
 		off += L;
 		}
+	std::vector<uint32_t> h_rb(na + 1, 0);
+	for (uint32_t s = 0; s < na; ++s)
+		h_rb[s + 1] = h_rb[s] + ctx->h_len[ids_a[s]];
 	std::vector<uint64_t> boff(nb);
 	uint64_t btot = 0;
 	for (uint32_t t = 0; t < nb; ++t)
@@ -831,7 +909,7 @@ int mb200_align_groups(mb200_ctx *ctx, uint32_t na, const uint32_t *ids_a, const
 				return mb_fail(ctx, MB200_EINVAL, "group B pos2col out of range");
 		btot += L;
 		}
-	const size_t maps = al256(c2p.size()*4) + al256(btot*4) + al256(nb*8) + al256(na*4) + al256(nb*4);
+	const size_t maps = al256(c2p.size()*4) + al256(btot*4) + al256(nb*8) + al256(na*4) + al256(nb*4) + al256((na + 1)*4);
 	const size_t jsz = join_scratch_bytes(cols_a, cols_b);
 	ENSURE(ctx->d_join, maps + jsz);
 	char *base = (char *) ctx->d_join.p;
@@ -840,7 +918,9 @@ int mb200_align_groups(mb200_ctx *ctx, uint32_t na, const uint32_t *ids_a, const
 	uint64_t *d_boff = (uint64_t *) base;            base += al256(nb*8);
 	uint32_t *d_ida = (uint32_t *) base;             base += al256(na*4);
 	uint32_t *d_idb = (uint32_t *) base;             base += al256(nb*4);
+	uint32_t *d_rb = (uint32_t *) base;              base += al256((na + 1)*4);
 	TRACE_MARK(5);
+	CU(cudaMemcpyAsync(d_rb, h_rb.data(), (na + 1)*4, cudaMemcpyHostToDevice, st));
 	CU(cudaMemcpyAsync(d_c2p, c2p.data(), c2p.size()*4, cudaMemcpyHostToDevice, st));
 	CU(cudaMemcpyAsync(d_p2cb, pos2col_b, btot*4, cudaMemcpyHostToDevice, st));
 	CU(cudaMemcpyAsync(d_boff, boff.data(), nb*8, cudaMemcpyHostToDevice, st));
@@ -849,7 +929,7 @@ int mb200_align_groups(mb200_ctx *ctx, uint32_t na, const uint32_t *ids_a, const
 	ctx->stats.h2d_bytes += c2p.size()*4 + btot*4 + nb*8 + (na + nb)*4;
 	TRACE_MARK(0);
 	JoinBufs B;
-	rc = join_core(ctx, na, nb, d_ida, d_idb, d_c2p, d_p2cb, d_boff, cols_a, cols_b, base, jsz, B, tmark);
+	rc = join_core(ctx, na, nb, d_ida, d_idb, d_c2p, d_p2cb, d_boff, d_rb, h_rb, cols_a, cols_b, base, jsz, B, tmark);
 	if (rc != MB200_OK)
 		return rc;
 	CU(cudaMemcpyAsync(path_out, B.path, cols_a + cols_b + 1, cudaMemcpyDeviceToHost, st));
@@ -902,6 +982,7 @@ int mb200_msa_join(mb200_ctx *ctx, uint32_t na, const uint32_t *ids_a, uint32_t 
 	std::vector<uint8_t> member(ctx->nseq, 0);
 	std::vector<uint32_t> ids(na + nb);
 	std::vector<uint64_t> boff(nb);
+	std::vector<uint32_t> h_rb(na + 1, 0);
 	uint32_t lmax = 0;
 	uint64_t btot = 0;
 	for (uint32_t m = 0; m < na + nb; ++m)
@@ -912,6 +993,8 @@ int mb200_msa_join(mb200_ctx *ctx, uint32_t na, const uint32_t *ids_a, uint32_t 
 		member[s] = 1;
 		ids[m] = s;
 		lmax = std::max(lmax, ctx->h_len[s]);
+		if (m < na)
+			h_rb[m + 1] = h_rb[m] + ctx->h_len[s];
 		if (m >= na)
 			{
 			boff[m - na] = btot;
@@ -927,7 +1010,8 @@ int mb200_msa_join(mb200_ctx *ctx, uint32_t na, const uint32_t *ids_a, uint32_t 
 			return mb_fail(ctx, MB200_EINVAL, "mb200_msa_join: group B members are not in one MSA");
 	const uint32_t cap = std::max(old_a, old_b);
 	// fixed part of the scratch: ids, boff, mark/remap [2][cap], map [2][cap], dims
-	const size_t fixed = al256((na + nb)*4) + al256(nb*8) + al256(2*(size_t) cap*4) + al256(2*(size_t) cap*4) + 256;
+	const size_t fixed = al256((na + nb)*4) + al256(nb*8) + al256(2*(size_t) cap*4) + al256(2*(size_t) cap*4) + 256
+	  + al256((na + 1)*4);
 	// upper bounds for the projected sizes are the old sizes
 	const size_t mapsz = al256((size_t) na*old_a*4) + al256(btot*4);
 	const size_t jsz = join_scratch_bytes(old_a, old_b);
@@ -938,11 +1022,13 @@ int mb200_msa_join(mb200_ctx *ctx, uint32_t na, const uint32_t *ids_a, uint32_t 
 	uint32_t *d_mark = (uint32_t *) base;            base += al256(2*(size_t) cap*4);
 	uint32_t *d_map = (uint32_t *) base;             base += al256(2*(size_t) cap*4);
 	uint32_t *d_dims = (uint32_t *) base;            base += 256;
+	uint32_t *d_rb = (uint32_t *) base;              base += al256((na + 1)*4);
 	int32_t *d_c2p = (int32_t *) base;               base += al256((size_t) na*old_a*4);
 	uint32_t *d_p2cb = (uint32_t *) base;            base += al256(btot*4);
 	TRACE_MARK(5);
 	CU(cudaMemcpyAsync(d_ids, ids.data(), (na + nb)*4, cudaMemcpyHostToDevice, st));
 	CU(cudaMemcpyAsync(d_boff, boff.data(), nb*8, cudaMemcpyHostToDevice, st));
+	CU(cudaMemcpyAsync(d_rb, h_rb.data(), (na + 1)*4, cudaMemcpyHostToDevice, st));
 	CU(cudaMemsetAsync(d_mark, 0, 2*(size_t) cap*4, st));
 	ctx->stats.h2d_bytes += (na + nb)*4 + nb*8;
 	MsaJob J;
@@ -968,7 +1054,7 @@ int mb200_msa_join(mb200_ctx *ctx, uint32_t na, const uint32_t *ids_a, uint32_t 
 	ctx->stats.kernel_launches += 3;
 	TRACE_MARK(0);
 	JoinBufs B;
-	rc = join_core(ctx, na, nb, d_ids, d_ids + na, d_c2p, d_p2cb, d_boff, cols_a, cols_b, base, jsz, B, tmark);
+	rc = join_core(ctx, na, nb, d_ids, d_ids + na, d_c2p, d_p2cb, d_boff, d_rb, h_rb, cols_a, cols_b, base, jsz, B, tmark);
 	if (rc != MB200_OK)
 		return rc;
 	J.path = B.path; J.plen = B.plen;
