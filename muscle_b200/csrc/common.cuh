@@ -40,30 +40,76 @@ __constant__ float4 c_logexp1[4] =
 //  * the reference's `smaller == LOG_ZERO` test is subsumed: if only the smaller is LOG_ZERO the gap
 //    is ~2e20 >= 7.5 and the larger is returned; if both are LOG_ZERO the gap is 0 and
 //    LOGEXP1(0)+LOG_ZERO rounds back to LOG_ZERO, the value the reference returns;
-//  * the piece is chosen by index into a 4-entry float4 table in shared memory (one LDS.128,
-//    conflict free: equal indexes broadcast, different indexes hit different banks).
+//  * the LOGEXP1 piece (cut points 1, 2.5, 4.5: all multiples of 1/2, intervals closed on the right)
+//    is found WITHOUT compares: k = ceil(2d) is formed in the mantissa of 2d + 1.5*2^23 by one
+//    FFMA with round-up, and k*16 added to a pre-biased base is the shared-memory address of a
+//    16-entry {c3,c2,c1,c0} table (k = 0..2 -> piece 0, 3..5 -> 1, 6..9 -> 2, 10..15 -> 3).  The load
+//    is predicated on d < 7.5 (for larger gaps the address is meaningless and the polynomial result is
+//    discarded by the final select).  Round 1 spent 8 of its 17 instructions per LOG_ADD on the
+//    half-rate ALU pipe (two compare/select pairs for the piece, min, max, gap test, select); this
+//    form is 14 instructions with 4 on the ALU pipe (profiles/r01_SUMMARY.md: ALU pipe 58 % busy).
+//  The arithmetic (sub, three mul/add Horner steps with separate roundings, final add) is written
+//  as explicit .rn PTX so that it can never be contracted into FMA.
+#define MB_LA_MAGIC_BITS 0x4B400000u        // bits of 12582912.0f = 1.5 * 2^23
 struct LogAdd
 	{
-	const float4 *coef;      // shared memory
+	uint32_t tab;       // shared-memory byte address of the table - (MB_LA_MAGIC_BITS << 4), kept opaque in a register
 	__device__ __forceinline__ float operator()(float x, float y) const
 		{
 		const float d = fabsf(__fsub_rn(x, y));
 		const float lo = fminf(x, y);
 		const float hi = fmaxf(x, y);
-		// piece index by a 2-step binary search (FSETP, FSEL, FSETP, SEL, predicated add)
-		const bool p2 = d > 2.5f;
-		const float thr = p2 ? 4.5f : 1.0f;
-		const float4 *a = p2 ? coef + 2 : coef;
-		if (d > thr)
-			a += 1;
-		const float4 c = *a;
-		float p = ADD(MUL(c.x, d), c.y);
-		p = ADD(MUL(p, d), c.z);
-		p = ADD(MUL(p, d), c.w);
-		const float r = ADD(p, lo);
-		return d >= 7.5f ? hi : r;
+#ifdef MB_LA_ASM
+		const float t = __fmaf_ru(d, 2.0f, 12582912.0f);
+		const uint32_t addr = tab + (__float_as_uint(t) << 4);
+		float r;
+		asm("{\n\t"
+		    ".reg .pred p;\n\t"
+		    ".reg .f32 c3, c2, c1, c0, q;\n\t"
+		    "setp.lt.f32 p, %1, 0f40F00000;\n\t"                      // d < 7.5
+		    "@p ld.shared.v4.f32 {c3, c2, c1, c0}, [%2];\n\t"
+		    "mul.rn.f32 q, c3, %1;\n\t"
+		    "add.rn.f32 q, q, c2;\n\t"
+		    "mul.rn.f32 q, q, %1;\n\t"
+		    "add.rn.f32 q, q, c1;\n\t"
+		    "mul.rn.f32 q, q, %1;\n\t"
+		    "add.rn.f32 q, q, c0;\n\t"
+		    "add.rn.f32 q, q, %3;\n\t"
+		    "selp.f32 %0, q, %4, p;\n\t"
+		    "}"
+		    : "=f"(r) : "f"(d), "r"(addr), "f"(lo), "f"(hi));
+#else
+		// the address stays inside the 17-entry table for any gap (entry 16 is never used for a result)
+		const float t = __fmaf_ru(fminf(d, 7.75f), 2.0f, 12582912.0f);
+		const uint32_t addr = tab + (__float_as_uint(t) << 4);
+		float4 c;
+		asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(c.x), "=f"(c.y), "=f"(c.z), "=f"(c.w) : "r"(addr));
+		float q = ADD(MUL(c.x, d), c.y);
+		q = ADD(MUL(q, d), c.z);
+		q = ADD(MUL(q, d), c.w);
+		const float r = d >= 7.5f ? hi : ADD(q, lo);
+#endif
+		return r;
 		}
 	};
+
+// builds the 16-entry table in shared memory (call with >= 16 threads, then __syncthreads) and
+// returns the functor
+__device__ __forceinline__ void mb_logadd_fill(float4 *tab16)
+	{
+	if (threadIdx.x < 17)
+		{
+		const int k = threadIdx.x;
+		tab16[k] = c_logexp1[k <= 2 ? 0 : (k <= 5 ? 1 : (k <= 9 ? 2 : 3))];
+		}
+	}
+__device__ __forceinline__ LogAdd mb_logadd_make(const float4 *tab16)
+	{
+	uint32_t base = (uint32_t) __cvta_generic_to_shared(tab16) - (MB_LA_MAGIC_BITS << 4);
+	asm volatile("mov.u32 %0, %0;" : "+r"(base));          // opaque: keeps the biased base in one register
+	LogAdd la = { base };
+	return la;
+	}
 
 // ---------------------------------------------------------------------------------------------
 // expf with glibc's result.  The reference computes the posterior with the host libm's expf

@@ -44,7 +44,7 @@
 
 struct PostSmemHdr
 	{
-	float4 coef[4];
+	float4 coef[17];      // LOGEXP1 pieces indexed by ceil(2*gap), see LogAdd
 	float  insT[MB_MAX_K];
 	};
 
@@ -67,15 +67,14 @@ k_posterior_sm(const PostParams P)
 	int   *aY = reinterpret_cast<int *>(aJX + CM*32);
 	float *aE = reinterpret_cast<float *>(aY) + CM*32;
 
-	if (threadIdx.x < 4)
-		sm.coef[threadIdx.x] = c_logexp1[threadIdx.x];
+	mb_logadd_fill(sm.coef);
 	for (int k = threadIdx.x; k < h.K; k += blockDim.x)
 		sm.insT[k] = P.insT[k];
 	for (int k = threadIdx.x; k < h.K*h.KS; k += blockDim.x)
 		matchT[k] = P.matchT[k];
 	__syncthreads();
 
-	const LogAdd la = { sm.coef };
+	const LogAdd la = mb_logadd_make(sm.coef);
 	const float Z = MB_LOG_ZERO;
 
 	float       *fm     = P.fm + (size_t) gwarp*P.fm_stride;
