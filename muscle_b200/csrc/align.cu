@@ -41,6 +41,7 @@
 
 // MB200_TRACE=1: wall-time split of the join path, printed at process exit
 static bool g_trace = false;
+static int g_trace_level = 0;          // 2: one line per join of >= 64 sequences
 static double g_t[6] = { 0, 0, 0, 0, 0, 0 };
 static unsigned g_calls = 0;
 static double now_s()
@@ -61,18 +62,21 @@ static void trace_init()
 	done = true;
 	g_trace = getenv("MB200_TRACE") != nullptr;
 	if (g_trace)
+		{
+		g_trace_level = atoi(getenv("MB200_TRACE"));
 		atexit(trace_report);
+		}
 	}
 
 // =============================================================================================
 // decoding DP
-#define AW_C 16                      // columns per lane
+#define AW_C 8                       // columns per lane
 #define AW_W (32*AW_C)               // strip width
 struct AlnProblem
 	{
 	uint32_t LX, LY, ld;             // ld: row pitch of dense (multiple of AW_C, padding zero)
 	const float *dense;              // LX rows x ld
-	uint32_t *tb;                    // traceback words [LX][nstrips*32] (global), unused when the launch keeps it in smem
+	uint16_t *tb;                    // traceback words [LX][nstrips*32] (global), unused when the launch keeps it in smem
 	float *edge;                     // 2*(LX+1) floats, strip hand-over (only read/written when LY > AW_W)
 	char *path;                      // LX+LY+1
 	float *score;
@@ -91,7 +95,7 @@ template <bool TB_SMEM>
 __global__ void __launch_bounds__(32*AW_MAXW)
 k_aln_wave(const AlnProblem *probs)
 	{
-	extern __shared__ uint32_t tb_sm[];
+	extern __shared__ uint16_t tb_sm[];
 	__shared__ float ring[AW_MAXW][AW_RING];
 	__shared__ int prog[AW_MAXW], cons[AW_MAXW];
 	__shared__ float finalS;
@@ -101,7 +105,7 @@ k_aln_wave(const AlnProblem *probs)
 	const int LX = (int) pr.LX, LY = (int) pr.LY;
 	const int nstrips = (LY + AW_W - 1)/AW_W;
 	const int npass = (nstrips + NW - 1)/NW;
-	uint32_t *tb = TB_SMEM ? tb_sm : pr.tb;
+	uint16_t *tb = TB_SMEM ? tb_sm : pr.tb;
 	volatile int *vprog = prog, *vcons = cons;
 	for (int pass = 0; pass < npass; ++pass)
 		{
@@ -127,12 +131,28 @@ k_aln_wave(const AlnProblem *probs)
 				old[c] = 0.0f;                                   // row 0 (calcalnflat.cpp:15-19)
 			float outNew = 0.0f, prevRecv = 0.0f;
 			const float *src = pr.dense + j0 + lane*AW_C;
-			float4 nx0, nx1, nx2, nx3;
-			nx0 = nx1 = nx2 = nx3 = make_float4(0.f, 0.f, 0.f, 0.f);
-			if (lane == 0 && LX >= 1)
+			// rows are fetched three steps ahead (a dependent L2 round trip is ~3 steps of arithmetic):
+			// before step t the queue holds rows i, i+1, i+2 of this lane (i = t - lane + 1)
+			float4 q0a, q0b, q1a, q1b, q2a, q2b;
+			q0a = q0b = q1a = q1b = q2a = q2b = make_float4(0.f, 0.f, 0.f, 0.f);
+			if (lane < nl)
 				{
-				const float4 *q = reinterpret_cast<const float4 *>(src);
-				nx0 = q[0]; nx1 = q[1]; nx2 = q[2]; nx3 = q[3];
+				const int r0 = 1 - lane;                         // row of step 0
+				if (r0 >= 1 && r0 <= LX)
+					{
+					const float4 *q = reinterpret_cast<const float4 *>(src + (size_t)(r0 - 1)*pr.ld);
+					q0a = q[0]; q0b = q[1];
+					}
+				if (r0 + 1 >= 1 && r0 + 1 <= LX)
+					{
+					const float4 *q = reinterpret_cast<const float4 *>(src + (size_t)(r0)*pr.ld);
+					q1a = q[0]; q1b = q[1];
+					}
+				if (r0 + 2 >= 1 && r0 + 2 <= LX)
+					{
+					const float4 *q = reinterpret_cast<const float4 *>(src + (size_t)(r0 + 1)*pr.ld);
+					q2a = q[0]; q2b = q[1];
+					}
 				}
 			const int nsteps = LX + nl - 1;
 			// the lane that owns DP column LY (for the final score)
@@ -159,13 +179,12 @@ k_aln_wave(const AlnProblem *probs)
 					}
 				const bool valid = i >= 1 && i <= LX && lane < nl;
 				float p[AW_C];
-				p[0] = nx0.x; p[1] = nx0.y; p[2] = nx0.z; p[3] = nx0.w; p[4] = nx1.x; p[5] = nx1.y; p[6] = nx1.z; p[7] = nx1.w;
-				p[8] = nx2.x; p[9] = nx2.y; p[10] = nx2.z; p[11] = nx2.w; p[12] = nx3.x; p[13] = nx3.y; p[14] = nx3.z; p[15] = nx3.w;
-				// prefetch the row this lane works on in the next step
-				if (lane < nl && i + 1 >= 1 && i + 1 <= LX)
+				p[0] = q0a.x; p[1] = q0a.y; p[2] = q0a.z; p[3] = q0a.w; p[4] = q0b.x; p[5] = q0b.y; p[6] = q0b.z; p[7] = q0b.w;
+				q0a = q1a; q0b = q1b; q1a = q2a; q1b = q2b;
+				if (lane < nl && i + 3 >= 1 && i + 3 <= LX)
 					{
-					const float4 *q = reinterpret_cast<const float4 *>(src + (size_t) i*pr.ld);
-					nx0 = q[0]; nx1 = q[1]; nx2 = q[2]; nx3 = q[3];
+					const float4 *q = reinterpret_cast<const float4 *>(src + (size_t)(i + 2)*pr.ld);
+					q2a = q[0]; q2b = q[1];
 					}
 				if (valid)
 					{
@@ -187,7 +206,7 @@ k_aln_wave(const AlnProblem *probs)
 							finalS = nw;
 						}
 					outNew = Y;
-					tb[((size_t)(i - 1)*nstrips + strip)*32 + lane] = word;
+					tb[((size_t)(i - 1)*nstrips + strip)*32 + lane] = (uint16_t) word;
 					if (hasOut && lane == 31)
 						{
 						if (ringOut)
@@ -210,7 +229,7 @@ k_aln_wave(const AlnProblem *probs)
 		}
 	// traceback (tracebackflat.cpp:3-37): TB(0,j) = 'Y', TB(i,0) = 'X'.  Warp 0, all lanes in lockstep
 	// on the same (i,j); the lanes hold the traceback words of 32 consecutive rows of the current
-	// 16-column group so that a dependent load is needed only every ~16 steps.
+	// 8-column group so that a dependent load is needed only every few steps.
 	if (wid != 0)
 		return;
 	uint32_t n = 0;
@@ -234,7 +253,7 @@ k_aln_wave(const AlnProblem *probs)
 					{
 					cbase = i; cidx = idx; d = 0;
 					const int r = i - lane;
-					cw = r >= 1 ? tb[(size_t)(r - 1)*nstrips*32 + idx] : 0u;
+					cw = r >= 1 ? (uint32_t) tb[(size_t)(r - 1)*nstrips*32 + idx] : 0u;
 					}
 				const uint32_t w = __shfl_sync(MB_FULL, cw, d);
 				const uint32_t code = (w >> (2*(jj % AW_C))) & 3u;
@@ -656,7 +675,7 @@ static inline size_t al256(size_t b) { return (b + 255)/256*256; }
 struct JoinBufs                       // carved out of ctx->d_join
 	{
 	float *post; uint32_t ld;
-	uint32_t *tb; float *edge; char *path; float *score; uint32_t *plen; AlnProblem *prob;
+	uint16_t *tb; float *edge; char *path; float *score; uint32_t *plen; AlnProblem *prob;
 	};
 
 // BuildPost + decoding DP of groups whose maps are already on the device.  Leaves path / plen /
@@ -669,11 +688,11 @@ static int join_core(mb200_ctx *ctx, uint32_t na, uint32_t nb, const uint32_t *d
 	const uint32_t ld = (cols_b + AW_C - 1)/AW_C*AW_C;
 	const uint32_t nstrips = (cols_b + AW_W - 1)/AW_W;
 	const size_t post_bytes = (size_t) cols_a*ld*sizeof(float);
-	const size_t tbw = (size_t) cols_a*nstrips*32*sizeof(uint32_t);
+	const size_t tbw = (size_t) cols_a*nstrips*32*sizeof(uint16_t);
 	const bool tb_smem = tbw <= 192*1024;
 	char *p = scratch;
 	B.post = (float *) p;            p += al256(post_bytes);
-	B.tb = (uint32_t *) p;           p += tb_smem ? 256 : al256(tbw);
+	B.tb = (uint16_t *) p;           p += tb_smem ? 256 : al256(tbw);
 	B.edge = (float *) p;            p += al256(2*((size_t) cols_a + 1)*sizeof(float));
 	B.path = p;                      p += al256((size_t) cols_a + cols_b + 16);
 	B.score = (float *) p;           p += 256;
@@ -744,7 +763,11 @@ static int join_core(mb200_ctx *ctx, uint32_t na, uint32_t nb, const uint32_t *d
 		k_aln_wave<false><<<1, 32*nwarps, 0, st>>>(B.prob);
 	CU(cudaGetLastError());
 	ctx->stats.kernel_launches++;
+	const double g1 = g_t[1], g2 = g_t[2], g3 = g_t[3];
 	TRACE_MARK(3);
+	if (g_trace_level >= 2 && na + nb >= 64)
+		fprintf(stderr, "[mb200 join] %u x %u seqs, %u x %u cols, %zu batch(es): DP %.2f ms (BuildPost totals so far: gather %.1f ms apply %.1f ms)\n",
+		  na, nb, cols_a, cols_b, cuts.size() - 1, 1e3*(g_t[3] - g3), 1e3*g1, 1e3*g2);
 	return MB200_OK;
 	}
 
@@ -752,7 +775,7 @@ static size_t join_scratch_bytes(uint32_t cols_a, uint32_t cols_b)
 	{
 	const uint32_t ld = (cols_b + AW_C - 1)/AW_C*AW_C;
 	const uint32_t nstrips = (cols_b + AW_W - 1)/AW_W;
-	return al256((size_t) cols_a*ld*4) + al256((size_t) cols_a*nstrips*32*4) + al256(2*((size_t) cols_a + 1)*4)
+	return al256((size_t) cols_a*ld*4) + al256((size_t) cols_a*nstrips*32*2) + al256(2*((size_t) cols_a + 1)*4)
 	  + al256((size_t) cols_a + cols_b + 16) + 4*256;
 	}
 
@@ -802,7 +825,7 @@ int mb200_align_pairs(mb200_ctx *ctx, uint32_t n, const uint32_t *store_pairs, c
 		const uint32_t ld = (LY + AW_C - 1)/AW_C*AW_C;
 		const uint32_t nstrips = (LY + AW_W - 1)/AW_W;
 		dense_total += al256((uint64_t) LX*ld*4);
-		tb_total += al256((uint64_t) LX*nstrips*32*4);
+		tb_total += al256((uint64_t) LX*nstrips*32*2);
 		edge_total += al256(2*((uint64_t) LX + 1)*4);
 		lxmax = std::max(lxmax, LX);
 		maxstrips = std::max(maxstrips, nstrips);
@@ -828,7 +851,7 @@ int mb200_align_pairs(mb200_ctx *ctx, uint32_t n, const uint32_t *store_pairs, c
 		AlnProblem &q = probs[k];
 		q.LX = LX; q.LY = LY; q.ld = ld;
 		q.dense = (const float *)(d_dense + od);
-		q.tb = (uint32_t *)(d_tb + ot);
+		q.tb = (uint16_t *)(d_tb + ot);
 		q.edge = (float *)(d_edge + oe);
 		q.path = d_paths + path_off[k];
 		q.score = d_scores + k;
@@ -839,7 +862,7 @@ int mb200_align_pairs(mb200_ctx *ctx, uint32_t n, const uint32_t *store_pairs, c
 		j.dense = (float *)(d_dense + od);
 		j.LX = LX; j.ld = ld;
 		od += al256((uint64_t) LX*ld*4);
-		ot += al256((uint64_t) LX*nstrips*32*4);
+		ot += al256((uint64_t) LX*nstrips*32*2);
 		oe += al256(2*((uint64_t) LX + 1)*4);
 		}
 	CU(cudaMemsetAsync(d_dense, 0, dense_total, st));

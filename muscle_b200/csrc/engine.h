@@ -64,7 +64,6 @@ struct mb200_ctx
 	// relax work order (pairs of [p_lo,p_hi) in 2-D tile order) and the range it was built for
 	DevBuf d_relax_order;
 	uint32_t relax_order_n = 0, relax_order_lo = 0, relax_order_hi = 0;
-	uint32_t relax_wcap = 0;          // most mask words of one operand (pair, orientation)
 	DevBuf d_tmp, d_tmp2;
 	// device-resident MSAs (align.cu): position -> column of every residue
 	// (same layout as d_codes) and, on the host, the column count of the MSA each sequence is in

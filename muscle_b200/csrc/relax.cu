@@ -31,7 +31,6 @@
 #include "engine.h"
 #include <cub/cub.cuh>
 #include <thrust/iterator/transform_iterator.h>
-#include <cuda_pipeline.h>
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
@@ -115,19 +114,6 @@ __global__ void k_mask_fill(uint32_t npairs, const uint64_t *__restrict__ rowbas
 		}
 	}
 
-// largest number of mask words of one operand (pair, orientation): sizes the stage of k_relax_st
-__global__ void k_max_words(uint32_t npairs, const uint64_t *__restrict__ rowbase, const uint2 *__restrict__ hdr,
-  uint32_t *__restrict__ out)
-	{
-	uint32_t best = 0;
-	for (uint32_t k = blockIdx.x*blockDim.x + threadIdx.x; k < npairs; k += gridDim.x*blockDim.x)
-		best = max(best, hdr[rowbase[k + 1] - 1].x - hdr[rowbase[k]].x);
-	for (int o = 16; o > 0; o >>= 1)
-		best = max(best, __shfl_xor_sync(MB_FULL, best, o));
-	if ((threadIdx.x & 31) == 0 && best > 0)
-		atomicMax(out, best);
-	}
-
 struct WidenU32
 	{
 	__host__ __device__ uint64_t operator()(uint32_t v) const { return v; }
@@ -186,18 +172,7 @@ int mb_store_build_masks(mb200_ctx *ctx)
 	  (const uint32_t *) ctx->d_tr_rowoff.p, (const mb200_entry *) ctx->d_tr_entries.p, ctx->d_tr_mk_hdr, ctx->d_tr_mk_words);
 	if (rc != MB200_OK)
 		return rc;
-	// stage capacity of k_relax_st: the widest operand of either orientation
-	ENSURE(ctx->d_tmp, 256);
-	CU(cudaMemsetAsync(ctx->d_tmp.p, 0, 4, ctx->stream));
-	k_max_words<<<ctx->prop.multiProcessorCount*4, 256, 0, ctx->stream>>>(np, (const uint64_t *) ctx->d_rowbase.p,
-	  (const uint2 *) ctx->d_mk_hdr.p, (uint32_t *) ctx->d_tmp.p);
-	k_max_words<<<ctx->prop.multiProcessorCount*4, 256, 0, ctx->stream>>>(np, (const uint64_t *) ctx->d_tr_rowbase.p,
-	  (const uint2 *) ctx->d_tr_mk_hdr.p, (uint32_t *) ctx->d_tmp.p);
-	CU(cudaGetLastError());
-	CU(cudaMemcpyAsync(ctx->h_pinned + 8, ctx->d_tmp.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
 	CU(cudaStreamSynchronize(ctx->stream));
-	ctx->relax_wcap = ctx->h_pinned[8];
-	ctx->stats.kernel_launches += 2;
 	ctx->store_masks_valid = true;
 	return MB200_OK;
 	}
@@ -236,7 +211,10 @@ __device__ __forceinline__ uint32_t pair_index(uint32_t n, uint32_t a, uint32_t 
 	}
 
 // MINB: resident CTAs/SM the register allocation is bounded for (2: 115 registers, no spill; 3: 80,
-// 28 bytes spilled; 4: 64, 40 bytes spilled)
+// 28 bytes spilled; 4: 64, 40 bytes spilled).  Measured on C2 (ms per iteration): 208.7 / 153.5 / 123.7 --
+// the kernel is bound by gather latency, occupancy wins over spills; 4 is the default.  A variant
+// that staged the headers and words of each z in shared memory (cp.async double buffer, 2 barriers
+// per z) measured 179.4 ms and was dropped.
 template <int MINB>
 __global__ void __launch_bounds__(RELAX_THREADS, MINB)
 k_relax(const RelaxParams P)
@@ -431,253 +409,6 @@ k_relax(const RelaxParams P)
 		}
 	}
 
-// ---------------------------------------------------------------------------------------------
-// k_relax_st: the same computation with the row headers and mask words of the CURRENT z staged in
-// shared memory.  For one z a CTA needs two contiguous arrays per operand (headers of all rows,
-// words of all rows): they are fetched with coalesced cp.async copies one z ahead (double buffer),
-// so the only dependent global accesses left in the inner loop are the ~0.7 value pairs per
-// (entry, z).  Profile of k_relax (direct gathers, round 2): 20.7 long-scoreboard stall cycles per
-// issue, L1 hit rate 75 %, L2 50 % -- three dependent gathers per (entry, z) with at most 1024
-// threads per SM resident.  Used when the stage fits (sequence lengths up to ~1000); longer inputs
-// take k_relax.
-#define RELAX_ST_THREADS 512
-#define RELAX_ST_EPT 4
-
-struct ZDescS
-	{
-	const uint2 *hdrA, *hdrB, *wA, *wB;          // global sources of the stage
-	const mb200_entry *enA, *enB;
-	uint32_t wloA, wloB, nWA, nWB;               // first word slot and word count of each operand
-	};
-
-struct RelaxStParams
-	{
-	RelaxParams R;
-	uint32_t lcap, wcap;                         // stage capacity: rows and words per operand
-	};
-
-__global__ void __launch_bounds__(RELAX_ST_THREADS, 2)
-k_relax_st(const RelaxStParams PS)
-	{
-	extern __shared__ __align__(16) unsigned char rs_smem[];
-	__shared__ ZDescS zd[RELAX_ZCHUNK];
-	const RelaxParams &P = PS.R;
-	if (blockIdx.x >= P.nwork)
-		return;
-	const uint32_t p = P.order[blockIdx.x];
-	const uint32_t n = P.n;
-	uint32_t x = 0;
-		{
-		const double nn = (double) n - 0.5;
-		double est = nn - sqrt(fmax(0.0, nn*nn - 2.0*(double) p));
-		x = (uint32_t) fmin(fmax(est, 0.0), (double)(n - 2));
-		while (x > 0 && (uint64_t) x*n - (uint64_t) x*(x + 1)/2 > p)
-			--x;
-		while (x + 1 < n - 1 && (uint64_t)(x + 1)*n - (uint64_t)(x + 1)*(x + 2)/2 <= p)
-			++x;
-		}
-	const uint32_t y = x + 1 + (p - (uint32_t)((uint64_t) x*n - (uint64_t) x*(x + 1)/2));
-	const uint32_t LX = P.seqlen[x], LY = P.seqlen[y];
-	const uint32_t *ro = P.rowoff + P.rowbase[p];
-	const uint64_t eb = P.entbase[p];
-	const mb200_entry *en = P.entries + eb;
-	mb200_entry *out = P.out + eb;
-	const uint32_t nnz = ro[LX];
-	const float fn = (float) n;
-	// stage buffer b: [hdrA lcap][hdrB lcap][wordsA wcap][wordsB wcap] uint2
-	const uint32_t bufElems = 2*PS.lcap + 2*PS.wcap;
-	uint2 *stage = reinterpret_cast<uint2 *>(rs_smem);
-
-	for (uint32_t e0 = 0; e0 < nnz; e0 += RELAX_ST_THREADS*RELAX_ST_EPT)
-		{
-		uint32_t ei[RELAX_ST_EPT], ej[RELAX_ST_EPT];
-		float acc[RELAX_ST_EPT];
-		bool live[RELAX_ST_EPT];
-#pragma unroll
-		for (int q = 0; q < RELAX_ST_EPT; ++q)
-			{
-			const uint32_t e = e0 + q*RELAX_ST_THREADS + threadIdx.x;
-			live[q] = e < nnz;
-			ei[q] = 0; ej[q] = 0; acc[q] = 0.0f;
-			if (live[q])
-				{
-				const mb200_entry v = en[e];
-				ej[q] = v.col;
-				acc[q] = __fmul_rn(v.p, 2.0f);          // Z=X and Z=Y (conspairflat.cpp:26-30)
-				uint32_t lo = 0, hi = LX;
-				while (hi - lo > 1)
-					{
-					const uint32_t mid = (lo + hi) >> 1;
-					if (ro[mid] <= e) lo = mid; else hi = mid;
-					}
-				ei[q] = lo;
-				}
-			}
-		for (uint32_t z0 = 0; z0 < n; z0 += RELAX_ZCHUNK)
-			{
-			__syncthreads();
-			if (threadIdx.x < RELAX_ZCHUNK)
-				{
-				const uint32_t z = z0 + threadIdx.x;
-				ZDescS d;
-				d.hdrA = nullptr;
-				if (z < n && z != x && z != y)
-					{
-					const uint32_t LZ = P.seqlen[z];
-					(void) LZ;
-					const uint2 *wordsA, *wordsB;
-					if (x < z)
-						{
-						const uint32_t q = pair_index(n, x, z);
-						d.hdrA = P.hdr + P.rowbase[q]; wordsA = P.words; d.enA = P.entries + P.entbase[q];
-						}
-					else
-						{
-						const uint32_t q = pair_index(n, z, x);
-						d.hdrA = P.trhdr + P.trbase[q]; wordsA = P.trwords; d.enA = P.trentries + P.entbase[q];
-						}
-					if (y < z)
-						{
-						const uint32_t q = pair_index(n, y, z);
-						d.hdrB = P.hdr + P.rowbase[q]; wordsB = P.words; d.enB = P.entries + P.entbase[q];
-						}
-					else
-						{
-						const uint32_t q = pair_index(n, z, y);
-						d.hdrB = P.trhdr + P.trbase[q]; wordsB = P.trwords; d.enB = P.trentries + P.entbase[q];
-						}
-					// the slot of the sentinel row (index = row count) is the end of the operand's words
-					d.wloA = d.hdrA[0].x; d.nWA = d.hdrA[LX].x - d.wloA;
-					d.wloB = d.hdrB[0].x; d.nWB = d.hdrB[LY].x - d.wloB;
-					d.wA = wordsA + d.wloA; d.wB = wordsB + d.wloB;
-					}
-				zd[threadIdx.x] = d;
-				}
-			__syncthreads();
-			const uint32_t zn = min((uint32_t) RELAX_ZCHUNK, n - z0);
-			// software pipeline over the z of the chunk: stage(zz+1) is in flight while zz is computed
-			auto issue = [&](uint32_t zz, uint32_t b)
-				{
-				const ZDescS &d = zd[zz];
-				if (d.hdrA != nullptr)
-					{
-					uint2 *dst = stage + (size_t) b*bufElems;
-					for (uint32_t k = threadIdx.x; k < LX; k += RELAX_ST_THREADS)
-						__pipeline_memcpy_async(dst + k, d.hdrA + k, 8);
-					dst += PS.lcap;
-					for (uint32_t k = threadIdx.x; k < LY; k += RELAX_ST_THREADS)
-						__pipeline_memcpy_async(dst + k, d.hdrB + k, 8);
-					dst += PS.lcap;
-					for (uint32_t k = threadIdx.x; k < d.nWA; k += RELAX_ST_THREADS)
-						__pipeline_memcpy_async(dst + k, d.wA + k, 8);
-					dst += PS.wcap;
-					for (uint32_t k = threadIdx.x; k < d.nWB; k += RELAX_ST_THREADS)
-						__pipeline_memcpy_async(dst + k, d.wB + k, 8);
-					}
-				__pipeline_commit();
-				};
-			issue(0, 0);
-			for (uint32_t zz = 0; zz < zn; ++zz)
-				{
-				const uint32_t b = zz & 1;
-				if (zz + 1 < zn)
-					issue(zz + 1, b ^ 1);
-				else
-					__pipeline_commit();
-				__pipeline_wait_prior(1);
-				__syncthreads();                                   // stage(zz) visible to every thread
-				const ZDescS d = zd[zz];
-				if (d.hdrA != nullptr)
-					{
-					const uint2 *shA = stage + (size_t) b*bufElems;
-					const uint2 *shB = shA + PS.lcap;
-					const uint2 *swA = shB + PS.lcap;
-					const uint2 *swB = swA + PS.wcap;
-					uint2 a[RELAX_ST_EPT], bw[RELAX_ST_EPT];
-					uint32_t sA[RELAX_ST_EPT], sB[RELAX_ST_EPT], lo[RELAX_ST_EPT], hi[RELAX_ST_EPT], m[RELAX_ST_EPT];
-					float pa[RELAX_ST_EPT], pb[RELAX_ST_EPT];
-#pragma unroll
-					for (int q = 0; q < RELAX_ST_EPT; ++q)
-						{
-						uint2 hA = make_uint2(0u, 0u), hB = make_uint2(0u, 0u);
-						if (live[q])
-							{
-							hA = shA[ei[q]];
-							hB = shB[ej[q]];
-							}
-						const uint32_t w0A = hA.y & 0xffffu, w0B = hB.y & 0xffffu;
-						lo[q] = max(w0A, w0B);
-						hi[q] = min(w0A + (hA.y >> 16), w0B + (hB.y >> 16));
-						sA[q] = hA.x - d.wloA - w0A;                 // word w of the row is swA[sA + w]
-						sB[q] = hB.x - d.wloB - w0B;
-						a[q] = make_uint2(0u, 0u); bw[q] = make_uint2(0u, 0u);
-						if (lo[q] < hi[q])
-							{
-							a[q] = swA[sA[q] + lo[q]];
-							bw[q] = swB[sB[q] + lo[q]];
-							}
-						m[q] = a[q].x & bw[q].x;
-						pa[q] = 0.0f; pb[q] = 0.0f;
-						if (m[q])
-							{
-							const uint32_t below = (m[q] & (0u - m[q])) - 1u;
-							pa[q] = d.enA[a[q].y + __popc(a[q].x & below)].p;
-							pb[q] = d.enB[bw[q].y + __popc(bw[q].x & below)].p;
-							}
-						}
-#pragma unroll
-					for (int q = 0; q < RELAX_ST_EPT; ++q)
-						{
-						float s = acc[q];
-						if (m[q])
-							{
-							s = __fadd_rn(s, __fmul_rn(pa[q], pb[q]));                 // relaxflat.cpp:27,56,90
-							uint32_t mm = m[q] & (m[q] - 1u);
-							while (mm)
-								{
-								const uint32_t below = (mm & (0u - mm)) - 1u;
-								const float xa = d.enA[a[q].y + __popc(a[q].x & below)].p;
-								const float xb = d.enB[bw[q].y + __popc(bw[q].x & below)].p;
-								s = __fadd_rn(s, __fmul_rn(xa, xb));
-								mm &= mm - 1u;
-								}
-							}
-						for (uint32_t w = lo[q] + 1; w < hi[q]; ++w)
-							{
-							const uint2 a2 = swA[sA[q] + w];
-							const uint2 b2 = swB[sB[q] + w];
-							uint32_t mm = a2.x & b2.x;
-							while (mm)
-								{
-								const uint32_t below = (mm & (0u - mm)) - 1u;
-								const float xa = d.enA[a2.y + __popc(a2.x & below)].p;
-								const float xb = d.enB[b2.y + __popc(b2.x & below)].p;
-								s = __fadd_rn(s, __fmul_rn(xa, xb));
-								mm &= mm - 1u;
-								}
-							}
-						acc[q] = s;
-						}
-					}
-				__syncthreads();                                   // everyone done with buffer b before it is refilled
-				}
-			__pipeline_wait_prior(0);
-			}
-#pragma unroll
-		for (int q = 0; q < RELAX_ST_EPT; ++q)
-			{
-			if (live[q])
-				{
-				const uint32_t e = e0 + q*RELAX_ST_THREADS + threadIdx.x;
-				mb200_entry v;
-				v.col = ej[q];
-				v.p = __fdiv_rn(acc[q], fn);                    // mysparsemx.cpp:108
-				out[e] = v;
-				}
-			}
-		}
-	}
-
 // copy entries of pairs outside [p_lo,p_hi) unchanged into the new buffer
 __global__ void k_copy_entries(uint64_t lo, uint64_t hi, const mb200_entry *__restrict__ src, mb200_entry *__restrict__ dst)
 	{
@@ -767,27 +498,12 @@ int mb200_consistency_iter(mb200_ctx *ctx, uint32_t p_lo, uint32_t p_hi)
 		P.out = (mb200_entry *) ctx->d_entries2.p;
 		CU(cudaEventRecord(ctx->ev1, st));
 		static int occ = 0;
-		static int staged = -1;
 		if (occ == 0)
 			{
 			const char *ev = getenv("MB200_RELAX_OCC");        // tuning hooks
 			occ = ev ? atoi(ev) : 4;
-			const char *sv = getenv("MB200_RELAX_STAGED");
-			staged = sv ? atoi(sv) : 1;
 			}
-		uint32_t lmax = 0;
-		for (uint32_t i = 0; i < n; ++i)
-			lmax = std::max(lmax, ctx->h_len[i]);
-		const uint32_t lcap = (lmax + 1 + 1) & ~1u, wcap = (ctx->relax_wcap + 1) & ~1u;
-		const size_t st_smem = 2*(size_t)(2*lcap + 2*wcap)*sizeof(uint2);
-		if (staged && st_smem <= 100*1024)
-			{
-			RelaxStParams PS;
-			PS.R = P; PS.lcap = lcap; PS.wcap = wcap;
-			CU(cudaFuncSetAttribute(k_relax_st, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) st_smem));
-			k_relax_st<<<p_hi - p_lo, RELAX_ST_THREADS, st_smem, st>>>(PS);
-			}
-		else if (occ == 2)
+		if (occ == 2)
 			k_relax<2><<<p_hi - p_lo, RELAX_THREADS, 0, st>>>(P);
 		else if (occ == 4)
 			k_relax<4><<<p_hi - p_lo, RELAX_THREADS, 0, st>>>(P);
