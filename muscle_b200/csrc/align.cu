@@ -27,6 +27,7 @@
 // them strictly in order, the entries of one sparse row in parallel.
 #include "engine.h"
 #include <cuda_pipeline.h>
+#include <cub/cub.cuh>
 #include <algorithm>
 #include <chrono>
 #include <cstdio>
@@ -91,13 +92,27 @@ struct AlnProblem
 // warps the same wavefront continues: strip w+1 consumes, row by row, the last column of strip w
 // through a shared-memory ring guarded by a progress counter, so a 5000 x 5000 join takes ~LX+32*strips
 // steps instead of LX*strips.
+// 64-bit shared-memory accesses that are guaranteed to be ONE transaction (value + row tag)
+__device__ __forceinline__ void ring_put(uint2 *slot, float v, int row)
+	{
+	asm volatile("st.volatile.shared.v2.u32 [%0], {%1, %2};" :: "r"((uint32_t) __cvta_generic_to_shared(slot)),
+	  "r"(__float_as_uint(v)), "r"((uint32_t) row) : "memory");
+	}
+__device__ __forceinline__ uint2 ring_get(const uint2 *slot)
+	{
+	uint2 e;
+	asm volatile("ld.volatile.shared.v2.u32 {%0, %1}, [%2];" : "=r"(e.x), "=r"(e.y)
+	  : "r"((uint32_t) __cvta_generic_to_shared(slot)) : "memory");
+	return e;
+	}
+
 template <bool TB_SMEM>
 __global__ void __launch_bounds__(32*AW_MAXW)
 k_aln_wave(const AlnProblem *probs)
 	{
 	extern __shared__ uint16_t tb_sm[];
-	__shared__ float ring[AW_MAXW][AW_RING];
-	__shared__ int prog[AW_MAXW], cons[AW_MAXW];
+	__shared__ uint2 ring[AW_MAXW][AW_RING];          // {bits of the value, row it belongs to}: one 8-byte store
+	__shared__ int cons[AW_MAXW];
 	__shared__ float finalS;
 	const AlnProblem pr = probs[blockIdx.x];
 	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -106,13 +121,13 @@ k_aln_wave(const AlnProblem *probs)
 	const int nstrips = (LY + AW_W - 1)/AW_W;
 	const int npass = (nstrips + NW - 1)/NW;
 	uint16_t *tb = TB_SMEM ? tb_sm : pr.tb;
-	volatile int *vprog = prog, *vcons = cons;
+	volatile int *vcons = cons;
 	for (int pass = 0; pass < npass; ++pass)
 		{
 		if (lane == 0)
-			{
-			prog[wid] = 0; cons[wid] = 0;
-			}
+			cons[wid] = 0;
+		for (int k = lane; k < AW_RING; k += 32)
+			ring[wid][k] = make_uint2(0u, 0u);                 // row tags start at 1
 		__syncthreads();
 		const int strip = pass*NW + wid;
 		if (strip < nstrips)
@@ -168,9 +183,14 @@ k_aln_wave(const AlnProblem *probs)
 						{
 						if (ringIn)
 							{
-							while (vprog[wid - 1] < i)
-								;                                     // strip on the left has not produced row i yet
-							recv = ((volatile float *) ring[wid - 1])[i % AW_RING];
+							// value and row tag travel in one 64-bit shared-memory word, so no fence is needed
+							// (a __threadfence_block here waited for this lane's outstanding GLOBAL traceback
+							// store every step: 1 us per step in the first version)
+							uint2 e;
+							do
+								e = ring_get(&ring[wid - 1][i % AW_RING]);
+							while ((int) e.y != i);                   // strip on the left has not produced row i yet
+							recv = __uint_as_float(e.x);
 							vcons[wid] = i;
 							}
 						else
@@ -213,9 +233,7 @@ k_aln_wave(const AlnProblem *probs)
 							{
 							while (i > AW_RING && vcons[wid + 1] < i - AW_RING)
 								;                                     // the slot still holds an unconsumed row
-							((volatile float *) ring[wid])[i % AW_RING] = outNew;
-							__threadfence_block();
-							vprog[wid] = i;
+							ring_put(&ring[wid][i % AW_RING], outNew, i);
 							}
 						else
 							edgeOut[i] = outNew;
@@ -382,110 +400,145 @@ k_bp_gather(const BuildPostParams P, const BpStage G)
 		}
 	}
 
-// One warp per row (column of alignment A).  The (s,t) steps of one s are consumed in groups of
-// BP_G: while group g is applied, the 2 KB of slots of group g+1 are already on their way into the
-// other half of a shared-memory double buffer (cp.async), so the ordered accumulation never waits
-// on HBM; inside a step the <= 16 entries of the sparse row go to distinct columns and are added
-// by one lane each.
+// rows (columns of A) by descending number of members that have a residue there: the per-row chain of
+// (s,t) steps is strictly serial, so a join lasts at least as long as its heaviest row (a conserved
+// column: |A| x |B| steps); heavy rows must start first and light rows fill in behind them.
+__global__ void k_bp_weight(const BuildPostParams P, uint32_t *__restrict__ weight, uint32_t *__restrict__ rowid)
+	{
+	const uint32_t row = blockIdx.x*blockDim.x + threadIdx.x;
+	if (row >= P.cols_a)
+		return;
+	uint32_t w = 0;
+	for (uint32_t s = 0; s < P.na; ++s)
+		w += P.col2pos_a[(size_t) s*P.cols_a + row] >= 0 ? 1u : 0u;
+	weight[row] = w;
+	rowid[row] = row;
+	}
+
+#define BP_NBUF 3
+struct BpSched
+	{
+	const uint32_t *order;    // rows, heaviest first
+	uint32_t *cursor;         // work cursor of this launch (zeroed by the host)
+	};
+
+// Persistent warps, one row (column of alignment A) at a time, heaviest rows first.  The (s,t)
+// steps of one s are consumed in groups of BP_G: while group g is applied, the slots of groups g+1
+// and g+2 are already on their way into a shared-memory ring (cp.async), so the ordered accumulation
+// never waits on HBM; inside a step the <= 16 entries of the sparse row go to distinct columns and
+// are added by one lane each.
 __global__ void __launch_bounds__(32*BP_WARPS)
-k_bp_apply(const BuildPostParams P, const BpStage G)
+k_bp_apply(const BuildPostParams P, const BpStage G, const BpSched S)
 	{
 	extern __shared__ __align__(16) unsigned char bp_smem[];
 	const uint32_t wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
-	const uint32_t row = blockIdx.x*BP_WARPS + wib;
 	const size_t acc_bytes = ((size_t) BP_WARPS*P.cols_b*sizeof(float) + 15) & ~(size_t) 15;
 	float *acc = reinterpret_cast<float *>(bp_smem) + (size_t) wib*P.cols_b;
-	uint2 *stage = reinterpret_cast<uint2 *>(bp_smem + acc_bytes) + (size_t) wib*2*BP_G*BP_W;
-	if (row >= P.cols_a)
-		return;
-	float *prow = P.post + (size_t) row*P.ld;
-	for (uint32_t c = lane; c < P.cols_b; c += 32)
-		acc[c] = prow[c];
-	__syncwarp();
+	uint2 *stage = reinterpret_cast<uint2 *>(bp_smem + acc_bytes) + (size_t) wib*BP_NBUF*BP_G*BP_W;
 	const uint32_t ngroups = (P.nb + BP_G - 1)/BP_G;
-	for (uint32_t sl = 0; sl < G.s_n; ++sl)
+	const uint32_t rb0 = G.rb[G.s_lo];
+	for (;;)
 		{
-		const uint32_t s = G.s_lo + sl;
-		const int32_t pos = P.col2pos_a[(size_t) s*P.cols_a + row];
-		if (pos < 0)
-			continue;
-		const uint64_t base = (uint64_t)(G.rb[s] - G.rb[G.s_lo] + (uint32_t) pos)*P.nb;
-		// prologue: group 0 in flight
-		uint32_t cntNext = 0;
-		{
-		const uint32_t nt = min((uint32_t) BP_G, P.nb);
-		if (lane < nt)
-			cntNext = G.cnt[base + lane];
-		const uint4 *src = reinterpret_cast<const uint4 *>(G.slots + base*BP_W);
-		uint4 *dst = reinterpret_cast<uint4 *>(stage);
-		for (uint32_t q = lane; q < nt*(BP_W/2); q += 32)
-			__pipeline_memcpy_async(dst + q, src + q, 16);
-		__pipeline_commit();
-		}
-		for (uint32_t g = 0; g < ngroups; ++g)
+		uint32_t k = 0;
+		if (lane == 0)
+			k = atomicAdd(S.cursor, 1u);
+		k = __shfl_sync(MB_FULL, k, 0);
+		if (k >= P.cols_a)
+			break;
+		const uint32_t row = S.order[k];
+		float *prow = P.post + (size_t) row*P.ld;
+		for (uint32_t c = lane; c < P.cols_b; c += 32)
+			acc[c] = prow[c];
+		__syncwarp();
+		for (uint32_t sl0 = 0; sl0 < G.s_n; sl0 += 32)
 			{
-			const uint32_t t0 = g*BP_G;
-			const uint32_t nt = min((uint32_t) BP_G, P.nb - t0);
-			const uint32_t cntCur = cntNext;
-			cntNext = 0;
-			if (g + 1 < ngroups)
+			// which of the next 32 members have a residue in this column
+			int32_t myPos = -1;
+			if (sl0 + lane < G.s_n)
+				myPos = P.col2pos_a[(size_t)(G.s_lo + sl0 + lane)*P.cols_a + row];
+			uint32_t members = __ballot_sync(MB_FULL, myPos >= 0);
+			while (members)
 				{
-				const uint32_t t1 = t0 + BP_G;
-				const uint32_t nt1 = min((uint32_t) BP_G, P.nb - t1);
-				if (lane < nt1)
-					cntNext = G.cnt[base + t1 + lane];
-				const uint4 *src = reinterpret_cast<const uint4 *>(G.slots + (base + t1)*BP_W);
-				uint4 *dst = reinterpret_cast<uint4 *>(stage + (size_t)((g + 1) & 1)*BP_G*BP_W);
-				for (uint32_t q = lane; q < nt1*(BP_W/2); q += 32)
-					__pipeline_memcpy_async(dst + q, src + q, 16);
-				}
-			__pipeline_commit();
-			__pipeline_wait_prior(1);                          // group g has landed
-			__syncwarp();
-			const uint2 *cur = stage + (size_t)(g & 1)*BP_G*BP_W;
-			uint32_t rest = __ballot_sync(MB_FULL, lane < nt && cntCur != 0);
-			// 1-deep software pipeline over the steps of the group: the next step's entry is fetched
-			// from the stage before the current one is added
-			uint32_t l = rest ? (uint32_t) __ffs(rest) - 1 : 0;
-			uint32_t nl = __shfl_sync(MB_FULL, cntCur, l);
-			uint2 v = make_uint2(0u, 0u);
-			if (rest && nl != 255 && lane < nl)
-				v = cur[l*BP_W + lane];
-			while (rest)
-				{
-				rest &= rest - 1;
-				const uint32_t l2 = rest ? (uint32_t) __ffs(rest) - 1 : 0;
-				const uint32_t nl2 = __shfl_sync(MB_FULL, cntCur, l2);
-				uint2 v2 = make_uint2(0u, 0u);
-				if (rest && nl2 != 255 && lane < nl2)
-					v2 = cur[l2*BP_W + lane];
-				if (nl != 255)
+				const uint32_t u = (uint32_t) __ffs(members) - 1;
+				members &= members - 1;
+				const int32_t pos = __shfl_sync(MB_FULL, myPos, u);
+				const uint32_t s = G.s_lo + sl0 + u;
+				const uint64_t base = (uint64_t)(G.rb[s] - rb0 + (uint32_t) pos)*P.nb;
+				// issue the copy of group g into ring slot g % BP_NBUF; returns that group's counts
+				auto issue = [&](uint32_t g) -> uint32_t
 					{
-					if (lane < nl)
-						acc[v.x] = __fadd_rn(acc[v.x], __uint_as_float(v.y));        // += w1*w2*P, unit weights
-					}
-				else if (lane == 0)
-					{
-					// rare: more than BP_W entries in the sparse row -> gather directly, still in order
-					const uint32_t *ro;
-					const mb200_entry *en;
-					bp_operand(P, P.ids_a[s], P.ids_b[t0 + l], ro, en);
-					const uint32_t *p2c = P.p2c_b + P.p2c_b_off[t0 + l];
-					for (uint32_t e = ro[pos]; e < ro[pos + 1]; ++e)
+					uint32_t c = 0;
+					if (g < ngroups)
 						{
-						const uint32_t c2 = p2c[en[e].col];
-						acc[c2] = __fadd_rn(acc[c2], en[e].p);
+						const uint32_t t1 = g*BP_G;
+						const uint32_t nt1 = min((uint32_t) BP_G, P.nb - t1);
+						if (lane < nt1)
+							c = G.cnt[base + t1 + lane];
+						const uint4 *src = reinterpret_cast<const uint4 *>(G.slots + (base + t1)*BP_W);
+						uint4 *dst = reinterpret_cast<uint4 *>(stage + (size_t)(g % BP_NBUF)*BP_G*BP_W);
+						for (uint32_t q = lane; q < nt1*(BP_W/2); q += 32)
+							__pipeline_memcpy_async(dst + q, src + q, 16);
 						}
+					__pipeline_commit();
+					return c;
+					};
+				uint32_t cnt0 = issue(0), cnt1 = issue(1), cnt2 = 0;
+				for (uint32_t g = 0; g < ngroups; ++g)
+					{
+					const uint32_t t0 = g*BP_G;
+					const uint32_t nt = min((uint32_t) BP_G, P.nb - t0);
+					cnt2 = issue(g + 2);
+					__pipeline_wait_prior(2);                          // group g has landed
+					__syncwarp();
+					const uint32_t cntCur = cnt0;
+					cnt0 = cnt1; cnt1 = cnt2;
+					const uint2 *cur = stage + (size_t)(g % BP_NBUF)*BP_G*BP_W;
+					uint32_t rest = __ballot_sync(MB_FULL, lane < nt && cntCur != 0);
+					// 1-deep software pipeline over the steps of the group: the next step's entry is fetched
+					// from the stage before the current one is added
+					uint32_t l = rest ? (uint32_t) __ffs(rest) - 1 : 0;
+					uint32_t nl = __shfl_sync(MB_FULL, cntCur, l);
+					uint2 v = make_uint2(0u, 0u);
+					if (rest && nl != 255 && lane < nl)
+						v = cur[l*BP_W + lane];
+					while (rest)
+						{
+						rest &= rest - 1;
+						const uint32_t l2 = rest ? (uint32_t) __ffs(rest) - 1 : 0;
+						const uint32_t nl2 = __shfl_sync(MB_FULL, cntCur, l2);
+						uint2 v2 = make_uint2(0u, 0u);
+						if (rest && nl2 != 255 && lane < nl2)
+							v2 = cur[l2*BP_W + lane];
+						if (nl != 255)
+							{
+							if (lane < nl)
+								acc[v.x] = __fadd_rn(acc[v.x], __uint_as_float(v.y));        // += w1*w2*P, unit weights
+							}
+						else if (lane == 0)
+							{
+							// rare: more than BP_W entries in the sparse row -> gather directly, still in order
+							const uint32_t *ro;
+							const mb200_entry *en;
+							bp_operand(P, P.ids_a[s], P.ids_b[t0 + l], ro, en);
+							const uint32_t *p2c = P.p2c_b + P.p2c_b_off[t0 + l];
+							for (uint32_t e = ro[pos]; e < ro[pos + 1]; ++e)
+								{
+								const uint32_t c2 = p2c[en[e].col];
+								acc[c2] = __fadd_rn(acc[c2], en[e].p);
+								}
+							}
+						__syncwarp();
+						l = l2; nl = nl2; v = v2;
+						}
+					__syncwarp();
 					}
-				__syncwarp();
-				l = l2; nl = nl2; v = v2;
+				__pipeline_wait_prior(0);
 				}
-			__syncwarp();
 			}
-		__pipeline_wait_prior(0);
+		for (uint32_t c = lane; c < P.cols_b; c += 32)
+			prow[c] = acc[c];
+		__syncwarp();
 		}
-	for (uint32_t c = lane; c < P.cols_b; c += 32)
-		prow[c] = acc[c];
 	}
 
 // =============================================================================================
@@ -713,7 +766,7 @@ static int join_core(mb200_ctx *ctx, uint32_t na, uint32_t nb, const uint32_t *d
 	P.entbase = (const uint64_t *) ctx->d_entbase.p;
 	P.post = B.post;
 	// the accumulator rows of BP_WARPS warps + their cp.async double buffers must fit in shared memory
-	const size_t acc_smem = (((size_t) BP_WARPS*cols_b*sizeof(float) + 15) & ~(size_t) 15) + (size_t) BP_WARPS*2*BP_G*BP_W*sizeof(uint2);
+	const size_t acc_smem = (((size_t) BP_WARPS*cols_b*sizeof(float) + 15) & ~(size_t) 15) + (size_t) BP_WARPS*BP_NBUF*BP_G*BP_W*sizeof(uint2);
 	if (acc_smem > 220*1024)
 		return mb_fail(ctx, MB200_EOVERFLOW, "alignment with %u columns too wide for the BuildPost kernel", cols_b);
 	// batches of sequences of A sized so that the staging area (one slot per residue of the batch and
@@ -735,7 +788,29 @@ static int join_core(mb200_ctx *ctx, uint32_t na, uint32_t nb, const uint32_t *d
 	G.slots = (uint2 *) ctx->d_stage.p;
 	G.cnt = (uint8_t *)(G.slots + max_slots*BP_W);
 	G.rb = d_rb;
+	// row order: heaviest first (weights and the sorted ids live in d_tmp2 next to the cub scratch)
+	size_t sort_tb = 0;
+	cub::DeviceRadixSort::SortPairsDescending(nullptr, sort_tb, (const uint32_t *) nullptr, (uint32_t *) nullptr,
+	  (const uint32_t *) nullptr, (uint32_t *) nullptr, (int) cols_a, 0, 32, st);
+	const size_t wbytes = al256((size_t) cols_a*4);
+	ENSURE(ctx->d_tmp2, 4*wbytes + 256 + sort_tb);
+	uint32_t *d_w = (uint32_t *) ctx->d_tmp2.p;
+	uint32_t *d_id = (uint32_t *)((char *) ctx->d_tmp2.p + wbytes);
+	uint32_t *d_w2 = (uint32_t *)((char *) ctx->d_tmp2.p + 2*wbytes);
+	uint32_t *d_order = (uint32_t *)((char *) ctx->d_tmp2.p + 3*wbytes);
+	uint32_t *d_cursor = (uint32_t *)((char *) ctx->d_tmp2.p + 4*wbytes);
+	void *d_sortscratch = (char *) ctx->d_tmp2.p + 4*wbytes + 256;
+	k_bp_weight<<<(cols_a + 255)/256, 256, 0, st>>>(P, d_w, d_id);
+	cub::DeviceRadixSort::SortPairsDescending(d_sortscratch, sort_tb, d_w, d_w2, d_id, d_order, (int) cols_a, 0, 32, st);
+	CU(cudaGetLastError());
+	BpSched S;
+	S.order = d_order;
+	S.cursor = d_cursor;
 	CU(cudaFuncSetAttribute(k_bp_apply, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) acc_smem));
+	int occ = 0;
+	CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_bp_apply, 32*BP_WARPS, acc_smem));
+	const uint32_t ablocks = std::max<uint32_t>(1, std::min<uint32_t>((cols_a + BP_WARPS - 1)/BP_WARPS,
+	  (uint32_t) std::max(occ, 1)*ctx->prop.multiProcessorCount));
 	for (size_t b = 0; b + 1 < cuts.size(); ++b)
 		{
 		G.s_lo = cuts[b];
@@ -744,10 +819,12 @@ static int join_core(mb200_ctx *ctx, uint32_t na, uint32_t nb, const uint32_t *d
 		const uint32_t gblocks = (uint32_t) std::min<uint64_t>((total + 255)/256, (uint64_t) ctx->prop.multiProcessorCount*32);
 		k_bp_gather<<<gblocks, 256, 0, st>>>(P, G);
 		TRACE_MARK(1);
-		k_bp_apply<<<(cols_a + BP_WARPS - 1)/BP_WARPS, 32*BP_WARPS, acc_smem, st>>>(P, G);
+		CU(cudaMemsetAsync(d_cursor, 0, 4, st));
+		k_bp_apply<<<ablocks, 32*BP_WARPS, acc_smem, st>>>(P, G, S);
 		TRACE_MARK(2);
 		ctx->stats.kernel_launches += 2;
 		}
+	ctx->stats.kernel_launches += 2;
 	CU(cudaGetLastError());
 	AlnProblem pr;
 	pr.LX = cols_a; pr.LY = cols_b; pr.ld = ld; pr.dense = B.post; pr.tb = B.tb; pr.edge = B.edge;
