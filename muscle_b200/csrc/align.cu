@@ -172,7 +172,10 @@ k_aln_wave(const AlnProblem *probs)
 			const int nsteps = LX + nl - 1;
 			// the lane that owns DP column LY (for the final score)
 			const int lastLane = (LY - 1 - j0)/AW_C, lastC = (LY - 1 - j0) % AW_C;
-			for (int t = 0; t < nsteps; ++t)
+			// one wavefront step; (qa,qb) holds this lane's row of the step and is refilled with the row
+			// three steps ahead.  The loop is unrolled by 3 over the three register sets: rotating them
+			// with moves would make every step wait for the load issued one step earlier.
+			auto step = [&](const int t, float4 &qa, float4 &qb)
 				{
 				const int i = t - lane + 1;                      // 1-based row
 				float recv = __shfl_up_sync(MB_FULL, outNew, 1);
@@ -199,12 +202,11 @@ k_aln_wave(const AlnProblem *probs)
 					}
 				const bool valid = i >= 1 && i <= LX && lane < nl;
 				float p[AW_C];
-				p[0] = q0a.x; p[1] = q0a.y; p[2] = q0a.z; p[3] = q0a.w; p[4] = q0b.x; p[5] = q0b.y; p[6] = q0b.z; p[7] = q0b.w;
-				q0a = q1a; q0b = q1b; q1a = q2a; q1b = q2b;
+				p[0] = qa.x; p[1] = qa.y; p[2] = qa.z; p[3] = qa.w; p[4] = qb.x; p[5] = qb.y; p[6] = qb.z; p[7] = qb.w;
 				if (lane < nl && i + 3 >= 1 && i + 3 <= LX)
 					{
 					const float4 *q = reinterpret_cast<const float4 *>(src + (size_t)(i + 2)*pr.ld);
-					q2a = q[0]; q2b = q[1];
+					qa = q[0]; qb = q[1];
 					}
 				if (valid)
 					{
@@ -241,7 +243,18 @@ k_aln_wave(const AlnProblem *probs)
 					}
 				prevRecv = recv;
 				__syncwarp();
+				};
+			int t = 0;
+			for (; t + 2 < nsteps; t += 3)
+				{
+				step(t, q0a, q0b);
+				step(t + 1, q1a, q1b);
+				step(t + 2, q2a, q2b);
 				}
+			if (t < nsteps)
+				step(t, q0a, q0b);
+			if (t + 1 < nsteps)
+				step(t + 1, q1a, q1b);
 			}
 		__syncthreads();
 		}
@@ -336,10 +349,11 @@ struct BuildPostParams
 #define BP_W 16           // staged entries per sparse row (rows are 7.2 +- 3 long: ~0.1 % exceed 16)
 #define BP_G 16           // (s,t) steps per staged group
 
+#define BP_END  0xffffffffu       // column value of an unused slot entry
+#define BP_LONG 0xfffffffeu       // first entry of a slot whose sparse row is longer than BP_W (applied by direct gather)
 struct BpStage
 	{
-	uint2   *slots;      // [residue of the batch][t][BP_W]  (column of B, bits of P)
-	uint8_t *cnt;        // [residue][t]; 255 = row longer than BP_W (applied by direct gather)
+	uint2   *slots;      // [residue of the batch][t][BP_W]  (column of B, bits of P), unused entries = BP_END
 	uint32_t s_lo, s_n;  // batch of sequences of A
 	const uint32_t *rb;  // [na+1] residues of A's members before member s (slots exist for residues only:
 	                     // indexing by (column, s) would stage mostly gaps -- a 1000-row MSA of 350-residue
@@ -383,20 +397,25 @@ k_bp_gather(const BuildPostParams P, const BpStage G)
 		const mb200_entry *en;
 		bp_operand(P, P.ids_a[s], P.ids_b[t], ro, en);
 		const uint32_t e0 = ro[pos];
-		uint32_t n = ro[pos + 1] - e0;
+		const uint32_t n = ro[pos + 1] - e0;
+		uint2 *dst = G.slots + idx*BP_W;
 		if (n <= BP_W)
 			{
 			const uint32_t *p2c = P.p2c_b + P.p2c_b_off[t];
-			uint2 *dst = G.slots + idx*BP_W;
 			for (uint32_t k = 0; k < n; ++k)
 				{
 				const mb200_entry v = en[e0 + k];
 				dst[k] = make_uint2(p2c[v.col], __float_as_uint(v.p));
 				}
+			for (uint32_t k = n; k < BP_W; ++k)
+				dst[k] = make_uint2(BP_END, 0u);
 			}
 		else
-			n = 255;
-		G.cnt[idx] = (uint8_t) n;
+			{
+			dst[0] = make_uint2(BP_LONG, 0u);
+			for (uint32_t k = 1; k < BP_W; ++k)
+				dst[k] = make_uint2(BP_END, 0u);
+			}
 		}
 	}
 
@@ -464,54 +483,57 @@ k_bp_apply(const BuildPostParams P, const BpStage G, const BpSched S)
 				const int32_t pos = __shfl_sync(MB_FULL, myPos, u);
 				const uint32_t s = G.s_lo + sl0 + u;
 				const uint64_t base = (uint64_t)(G.rb[s] - rb0 + (uint32_t) pos)*P.nb;
-				// issue the copy of group g into ring slot g % BP_NBUF; returns that group's counts
-				auto issue = [&](uint32_t g) -> uint32_t
+				// issue the copy of group g into ring slot g % BP_NBUF
+				auto issue = [&](uint32_t g)
 					{
-					uint32_t c = 0;
 					if (g < ngroups)
 						{
 						const uint32_t t1 = g*BP_G;
 						const uint32_t nt1 = min((uint32_t) BP_G, P.nb - t1);
-						if (lane < nt1)
-							c = G.cnt[base + t1 + lane];
 						const uint4 *src = reinterpret_cast<const uint4 *>(G.slots + (base + t1)*BP_W);
 						uint4 *dst = reinterpret_cast<uint4 *>(stage + (size_t)(g % BP_NBUF)*BP_G*BP_W);
 						for (uint32_t q = lane; q < nt1*(BP_W/2); q += 32)
 							__pipeline_memcpy_async(dst + q, src + q, 16);
 						}
 					__pipeline_commit();
-					return c;
 					};
-				uint32_t cnt0 = issue(0), cnt1 = issue(1), cnt2 = 0;
+				issue(0);
+				issue(1);
 				for (uint32_t g = 0; g < ngroups; ++g)
 					{
 					const uint32_t t0 = g*BP_G;
 					const uint32_t nt = min((uint32_t) BP_G, P.nb - t0);
-					cnt2 = issue(g + 2);
+					issue(g + 2);
 					__pipeline_wait_prior(2);                          // group g has landed
 					__syncwarp();
-					const uint32_t cntCur = cnt0;
-					cnt0 = cnt1; cnt1 = cnt2;
 					const uint2 *cur = stage + (size_t)(g % BP_NBUF)*BP_G*BP_W;
-					uint32_t rest = __ballot_sync(MB_FULL, lane < nt && cntCur != 0);
+					// which steps of the group have entries at all (first entry of every slot)
+					uint32_t rest = __ballot_sync(MB_FULL, lane < nt && cur[lane*BP_W].x != BP_END);
 					// 1-deep software pipeline over the steps of the group: the next step's entry is fetched
 					// from the stage before the current one is added
-					uint32_t l = rest ? (uint32_t) __ffs(rest) - 1 : 0;
-					uint32_t nl = __shfl_sync(MB_FULL, cntCur, l);
-					uint2 v = make_uint2(0u, 0u);
-					if (rest && nl != 255 && lane < nl)
-						v = cur[l*BP_W + lane];
+					uint2 v = make_uint2(BP_END, 0u);
+					uint32_t l = 0;
+					if (rest)
+						{
+						l = (uint32_t) __ffs(rest) - 1;
+						if (lane < BP_W)
+							v = cur[l*BP_W + lane];
+						}
 					while (rest)
 						{
 						rest &= rest - 1;
-						const uint32_t l2 = rest ? (uint32_t) __ffs(rest) - 1 : 0;
-						const uint32_t nl2 = __shfl_sync(MB_FULL, cntCur, l2);
-						uint2 v2 = make_uint2(0u, 0u);
-						if (rest && nl2 != 255 && lane < nl2)
-							v2 = cur[l2*BP_W + lane];
-						if (nl != 255)
+						uint2 v2 = make_uint2(BP_END, 0u);
+						uint32_t l2 = 0;
+						if (rest)
 							{
-							if (lane < nl)
+							l2 = (uint32_t) __ffs(rest) - 1;
+							if (lane < BP_W)
+								v2 = cur[l2*BP_W + lane];
+							}
+						const bool isLong = __shfl_sync(MB_FULL, v.x, 0) == BP_LONG;
+						if (!isLong)
+							{
+							if (v.x != BP_END)
 								acc[v.x] = __fadd_rn(acc[v.x], __uint_as_float(v.y));        // += w1*w2*P, unit weights
 							}
 						else if (lane == 0)
@@ -528,7 +550,7 @@ k_bp_apply(const BuildPostParams P, const BpStage G, const BpSched S)
 								}
 							}
 						__syncwarp();
-						l = l2; nl = nl2; v = v2;
+						l = l2; v = v2;
 						}
 					__syncwarp();
 					}
@@ -771,7 +793,7 @@ static int join_core(mb200_ctx *ctx, uint32_t na, uint32_t nb, const uint32_t *d
 		return mb_fail(ctx, MB200_EOVERFLOW, "alignment with %u columns too wide for the BuildPost kernel", cols_b);
 	// batches of sequences of A sized so that the staging area (one slot per residue of the batch and
 	// member of B) stays below ~2 GB
-	const uint64_t budget_slots = (2048ull << 20)/(BP_W*sizeof(uint2) + 1);
+	const uint64_t budget_slots = (2048ull << 20)/(BP_W*sizeof(uint2));
 	uint64_t max_slots = 0;
 	std::vector<uint32_t> cuts(1, 0);
 	for (uint32_t s = 0; s < na; )
@@ -783,10 +805,9 @@ static int join_core(mb200_ctx *ctx, uint32_t na, uint32_t nb, const uint32_t *d
 		cuts.push_back(e);
 		s = e;
 		}
-	ENSURE(ctx->d_stage, max_slots*BP_W*sizeof(uint2) + max_slots + 256);
+	ENSURE(ctx->d_stage, max_slots*BP_W*sizeof(uint2) + 256);
 	BpStage G;
 	G.slots = (uint2 *) ctx->d_stage.p;
-	G.cnt = (uint8_t *)(G.slots + max_slots*BP_W);
 	G.rb = d_rb;
 	// row order: heaviest first (weights and the sorted ids live in d_tmp2 next to the cub scratch)
 	size_t sort_tb = 0;
