@@ -51,7 +51,8 @@ def main():
 	flag = torch.tensor([1 if ok else 0], device="cuda")
 	dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 	if rank == 0:
-		print("MGPU_CHECK", "OK" if int(flag.item()) == 1 else "FAIL", "world", dist.get_world_size(), "pairs", len(offs))
+		print("MGPU_CHECK", "OK" if int(flag.item()) == 1 else "FAIL", "world", dist.get_world_size(), "pairs", len(offs),
+		  "ranges", M._ranges, "timings", {k: round(float(v), 3) for k, v in M.timings.items()})
 	dist.barrier()
 	dist.destroy_process_group()
 	sys.exit(0 if int(flag.item()) == 1 else 1)
