@@ -174,6 +174,23 @@ int mb200_msa_join(mb200_ctx *ctx, uint32_t na, const uint32_t *ids_a, uint32_t 
                    uint32_t *cols_out, float *score_out, char *path_out, uint32_t path_cap);
 int mb200_msa_export(mb200_ctx *ctx, uint32_t n, const uint32_t *ids, uint32_t *pos2col_out, uint32_t *cols_out);
 
+/* ---- guide tree ------------------------------------------------------ */
+/* UPGMA5::FixEADistMx (upgma5.cpp:504-519, distance = 1 - EA) + UPGMA5::Run (upgma5.cpp:87-330) as
+ * MPCFlat::CalcGuideTree calls them (mpcflat.cpp:183-205) -- including the reference's nearest-
+ * neighbour bookkeeping and tie order, which decide the topology.  ea: host vector of the N(N-1)/2 EA
+ * values in all-pairs order (what mb200_posteriors_allpairs / mb200_group_posteriors_allpairs
+ * returned), or NULL to use the EA vector the posterior stage left on this device.  Outputs are host
+ * arrays of N-1 entries indexed by internal node (join order): children as node indexes (0..N-1
+ * leaves, N+k internal node k) and branch lengths -- exactly the arguments of Tree::Create
+ * (tree.cpp:1454).  Join order (guidetreejoinorder.cpp:103) is a traversal of that 2N-1 node tree
+ * and stays on the host. */
+#define MB200_LINKAGE_MIN    1      /* values of the reference's LINKAGE enum (types.h:11-15) */
+#define MB200_LINKAGE_MAX    2
+#define MB200_LINKAGE_AVG    3
+#define MB200_LINKAGE_BIASED 4
+int mb200_guide_tree(mb200_ctx *ctx, const float *ea, int linkage, uint32_t *left, uint32_t *right,
+                     float *left_len, float *right_len);
+
 /* ---- per-pair debug/parity surface -------------------------------------------------------- */
 /* CalcPost (calcpost.cpp:4-36) for one pair with the dense result copied to the host:
  * post_out[LX*LY] thresholded posterior (CalcPostFlat), fwd_m_out / bwd_m_out (may be NULL)

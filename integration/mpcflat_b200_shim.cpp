@@ -6,12 +6,14 @@
 //   MPCFlat::CalcPosteriors   (mpcflat.cpp:214-252)    -> mb200_group_posteriors_allpairs (all visible GPUs)
 //   MPCFlat::CalcPosterior    (calcposteriorflat.cpp:45-92, per-pair form used by -profalign/-profseq)
 //                                                      -> deferred; the batch runs before the first AlignAlns
+//   MPCFlat::CalcGuideTree    (mpcflat.cpp:183-205: UPGMA5::FixEADistMx + UPGMA5::Run, upgma5.cpp:504,87)
+//                                                      -> mb200_guide_tree (+ the reference's Tree::Create / PermTree)
 //   MPCFlat::ConsIter         (consflat.cpp:5-23)      -> mb200_group_consistency_iter
 //   MPCFlat::AlignAlns        (alnalnsflat.cpp:7-52)   -> mb200_align_groups (+ the reference's own gap insertion)
 //   MPCFlat::ProgressiveAlign (progalnflat.cpp:73-100) -> mb200_msa_reset + one mb200_msa_join per guide-tree join
 //   MPCFlat::Refine           (mpcflat.cpp:255-265) / RefineIter (refineflat.cpp:4-31)
 //                                                      -> one mb200_msa_join per bipartition (same rand() stream)
-// Everything else (FASTA I/O, dereplication, UPGMA guide tree, join order, sorting, MSA output) is the
+// Everything else (FASTA I/O, dereplication, Tree object and join order, sorting, MSA output) is the
 // reference's own code, untouched.  Errors keep the reference convention: Die() -> message +
 // exit(1) (myutils.cpp:883).  There is no CPU fallback: inputs the engine does not implement (Mega
 // feature profiles) stop with a message instead of silently running something else.
@@ -176,6 +178,49 @@ void MPCFlat::CalcPosterior(uint PairIndex)
 	{
 	(void) PairIndex;
 	g_Deferred = this;
+	}
+
+// mpcflat.cpp:183-205.  The numeric part (distance = 1 - EA, biased-linkage UPGMA with the reference's
+// nearest-neighbour bookkeeping) runs on the device; the Tree object, the optional permutation and
+// the -guidetreeout exit are the reference's own code.
+void MPCFlat::CalcGuideTree()
+	{
+	if (opt(randomchaintree))
+		{
+		CalcGuideTree_RandomChain();
+		return;
+		}
+	NeedStore(*this);
+	const uint SeqCount = GetSeqCount();
+	asserta(SeqCount >= 2 && SIZE(m_Labels) == SeqCount);
+	vector<float> EAs;
+	EAs.reserve(SIZE(m_Pairs));
+	for (uint i = 0; i < SeqCount; ++i)
+		for (uint j = i + 1; j < SeqCount; ++j)
+			EAs.push_back(m_DistMx[i][j]);
+	vector<uint> Left(SeqCount - 1), Right(SeqCount - 1), Ids(SeqCount);
+	vector<float> LeftLength(SeqCount - 1), RightLength(SeqCount - 1);
+	Check(mb200_guide_tree(g_Ctx, EAs.data(), MB200_LINKAGE_BIASED, Left.data(), Right.data(),
+	  LeftLength.data(), RightLength.data()), "mb200_guide_tree");
+	vector<char *> Names(SeqCount);
+	for (uint i = 0; i < SeqCount; ++i)
+		{
+		Ids[i] = i;
+		Names[i] = mystrsave(m_Labels[i].c_str());
+		}
+	m_GuideTree.Create(SeqCount, SeqCount - 2, Left.data(), Right.data(), LeftLength.data(), RightLength.data(),
+	  Ids.data(), Names.data());                       // as UPGMA5::Run does (upgma5.cpp:305-307)
+	for (uint i = 0; i < SeqCount; ++i)
+		myfree(Names[i]);
+	PermTree(m_GuideTree, m_TreePerm);
+	if (optset_guidetreeout)
+		{
+		const string &FN = opt(guidetreeout);
+		Progress("Saving guide tree [%s] to %s\n", TREEPERMToStr(m_TreePerm), FN.c_str());
+		m_GuideTree.ToFile(FN);
+		Progress("Quitting.\n");
+		exit(0);
+		}
 	}
 
 void MPCFlat::ConsIter(uint Iter)

@@ -278,6 +278,7 @@ int mb200_set_seqs(mb200_ctx *ctx, uint32_t nseq, const uint8_t *bytes, const ui
 	ctx->stats.d2h_bytes = 0;
 	ctx->store_valid = false;
 	ctx->store_allpairs = false;
+	ctx->ea_allpairs = false;
 	ctx->plan_valid = false;
 	ctx->last_used_entries = 0;
 	if (ctx->have_hmm)
@@ -544,6 +545,7 @@ int mb200_posteriors(mb200_ctx *ctx, uint32_t npairs, const uint32_t *pair_x, co
 	ctx->h_px.assign(pair_x, pair_x + npairs);
 	ctx->h_py.assign(pair_y, pair_y + npairs);
 	ctx->store_allpairs = false;
+	ctx->ea_allpairs = false;
 	ctx->store_valid = false;
 	ctx->plan_valid = false;
 	ctx->plan_is_allpairs = false;
@@ -597,6 +599,7 @@ int mb200_posteriors_allpairs(mb200_ctx *ctx, uint32_t p_lo, uint32_t p_hi, floa
 		ctx->plan_valid = false;
 		}
 	ctx->store_valid = false;
+	ctx->ea_allpairs = false;
 	ctx->plan_is_allpairs = true;
 	ctx->store_p_lo = p_lo;
 	ctx->store_p_hi = p_hi;
@@ -604,6 +607,7 @@ int mb200_posteriors_allpairs(mb200_ctx *ctx, uint32_t p_lo, uint32_t p_hi, floa
 	if (rc == MB200_OK)
 		{
 		ctx->store_allpairs = (p_lo == 0 && p_hi == npairs);
+		ctx->ea_allpairs = ctx->store_allpairs;
 		ctx->store_p_lo = p_lo;
 		ctx->store_p_hi = p_hi;
 		}
@@ -623,6 +627,7 @@ int mb200_calc_post_dense(mb200_ctx *ctx, uint32_t x, uint32_t y, float *post_ou
 	ctx->h_px.assign(1, x);
 	ctx->h_py.assign(1, y);
 	ctx->store_allpairs = false;
+	ctx->ea_allpairs = false;
 	ctx->store_valid = false;
 	ctx->plan_valid = false;
 	ctx->plan_is_allpairs = false;

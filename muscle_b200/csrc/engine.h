@@ -38,6 +38,7 @@ struct mb200_ctx
 	// the store: sparse posteriors of the listed pairs (replaces MPCFlat::m_SparsePosts1/2)
 	bool store_valid = false;
 	bool store_allpairs = false;      // holds all N(N-1)/2 pairs in reference order
+	bool ea_allpairs = false;         // d_ea holds the EA of all pairs (computed on this device)
 	uint32_t store_p_lo = 0, store_p_hi = 0;
 	bool store_packed = false;        // entries are packed in store order (entbase ascending, no holes)
 	bool store_tr_valid = false;      // transposed orientation + permutation built

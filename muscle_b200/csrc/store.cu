@@ -360,6 +360,7 @@ static int adopt_image(mb200_ctx *ctx, uint32_t p_lo, uint32_t p_hi, uint64_t n_
 	ctx->store_masks_valid = false;
 	ctx->tr_values_stale = false;
 	ctx->store_allpairs = (p_lo == 0 && p_hi == all);
+	ctx->ea_allpairs = false;          // the adopted image carries no EA values
 	ctx->plan_is_allpairs = false;
 	ctx->store_p_lo = p_lo;
 	ctx->store_p_hi = p_hi;

@@ -22,7 +22,7 @@ EXPORTS = [
 	"mb200_store_exchange_begin", "mb200_store_exchange_commit", "mb200_store_entries_ptr", "mb200_store_values_changed",
 	"mb200_group_create", "mb200_group_destroy", "mb200_group_last_error", "mb200_group_size", "mb200_group_ctx",
 	"mb200_group_set_hmm", "mb200_group_set_seqs", "mb200_group_posteriors_allpairs", "mb200_group_consistency_iter",
-	"mb200_group_get_stats", "mb200_msa_reset", "mb200_msa_join", "mb200_msa_export",
+	"mb200_group_get_stats", "mb200_msa_reset", "mb200_msa_join", "mb200_msa_export", "mb200_guide_tree",
 ]
 
 
@@ -306,6 +306,16 @@ class Engine:
 			out.append(buf[o:o + L].copy())
 			o += L
 		return out, cols
+
+	# ---- guide tree
+	def guide_tree(self, ea=None, linkage=4):
+		"""UPGMA on the device; ea None = the EA vector of the all-pairs store.  -> (left, right, left_len, right_len)"""
+		n = self.nseq
+		L, R = np.empty(n - 1, np.uint32), np.empty(n - 1, np.uint32)
+		LL, RL = np.empty(n - 1, np.float32), np.empty(n - 1, np.float32)
+		e = None if ea is None else np.ascontiguousarray(ea, np.float32)
+		self._ck(self.lib.mb200_guide_tree(self.h, _ptr(e), C.c_int(linkage), _ptr(L), _ptr(R), _ptr(LL), _ptr(RL)))
+		return L, R, LL, RL
 
 	def stats(self):
 		s = Stats()

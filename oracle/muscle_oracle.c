@@ -9,6 +9,7 @@
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
+#include <float.h>
 #ifdef _OPENMP
 #include <omp.h>
 #endif
@@ -576,4 +577,73 @@ void mo_buildpost(uint32_t n, const uint32_t *len,
 						post[(size_t) pos2col_a[s][entries[p][e].col]*cols_b + pos2col_b[t][i]] += w*entries[p][e].p;
 				}
 			}
+	}
+
+/* ------------------------------------------------------------------ guide tree
+ * UPGMA5::FixEADistMx (upgma5.cpp:504-519) + UPGMA5::Run (upgma5.cpp:87-330), sequential, as the
+ * reference: triangle subscript (upgma5.h:63-72), nearest-neighbour bookkeeping incl. the "nasty
+ * special case" (:248-259), strict `<` scans in ascending index order.  ea: N(N-1)/2 values, row-major
+ * i<j.  linkage: 1 min, 2 max, 3 avg, 4 biased (types.h:11-15).  Outputs: N-1 entries each. */
+static uint32_t tri(uint32_t a, uint32_t b) { return a >= b ? b + (a*(a - 1))/2 : a + (b*(b - 1))/2; }
+static float avg2(float x, float y) { return (x + y)/2; }
+int mo_upgma(uint32_t n, const float *ea, int linkage, uint32_t *left, uint32_t *right, float *llen, float *rlen)
+	{
+	const uint32_t NONE = 0xffffffffu;
+	float *dist = (float *) malloc(sizeof(float)*((size_t) n*(n - 1)/2 + 1));
+	float *mind = (float *) malloc(sizeof(float)*n), *height = (float *) malloc(sizeof(float)*n);
+	uint32_t *nn = (uint32_t *) malloc(4*n), *node = (uint32_t *) malloc(4*n);
+	for (uint32_t i = 0; i < n; ++i)
+		{
+		mind[i] = FLT_MAX; nn[i] = NONE; node[i] = i;
+		}
+	for (uint32_t i = 1; i < n; ++i)
+		for (uint32_t j = 0; j < i; ++j)
+			{
+			const float e = ea[pair_index(n, j, i)];
+			if (!(e >= 0 && e <= 1))
+				return -1;
+			float d = 1 - e;
+			if (d < 0)
+				d = 0;
+			dist[tri(i, j)] = d;
+			if (d < mind[i]) { mind[i] = d; nn[i] = j; }
+			if (d < mind[j]) { mind[j] = d; nn[j] = i; }
+			}
+	for (uint32_t k = 0; k + 1 < n; ++k)
+		{
+		uint32_t lmin = NONE, rmin = NONE;
+		float best = FLT_MAX;
+		for (uint32_t j = 0; j < n; ++j)
+			{
+			if (node[j] == NONE)
+				continue;
+			if (mind[j] < best) { best = mind[j]; lmin = j; rmin = nn[j]; }
+			}
+		float newmin = FLT_MAX;
+		uint32_t newnn = NONE;
+		for (uint32_t j = 0; j < n; ++j)
+			{
+			if (j == lmin || j == rmin || node[j] == NONE)
+				continue;
+			const float dL = dist[tri(lmin, j)], dR = dist[tri(rmin, j)];
+			float nd;
+			if (linkage == 3) nd = avg2(dL, dR);
+			else if (linkage == 1) nd = dL < dR ? dL : dR;
+			else if (linkage == 2) nd = dL > dR ? dL : dR;
+			else nd = 0.1f*avg2(dL, dR) + (1 - 0.1f)*(dR < dL ? dR : dL);
+			if (nn[j] == rmin)
+				nn[j] = lmin;
+			dist[tri(lmin, j)] = nd;
+			if (nd < newmin) { newmin = nd; newnn = j; }
+			}
+		const float h = dist[tri(lmin, rmin)]/2;
+		const uint32_t uL = node[lmin], uR = node[rmin];
+		left[k] = uL; right[k] = uR;
+		llen[k] = h - (uL < n ? 0 : height[uL - n]);
+		rlen[k] = h - (uR < n ? 0 : height[uR - n]);
+		height[k] = h;
+		node[lmin] = n + k; nn[lmin] = newnn; mind[lmin] = newmin; node[rmin] = NONE;
+		}
+	free(dist); free(mind); free(height); free(nn); free(node);
+	return 0;
 	}

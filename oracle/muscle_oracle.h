@@ -76,6 +76,9 @@ void mo_buildpost(uint32_t n, const uint32_t *len,
   uint32_t nb, const uint32_t *ids_b, const uint32_t *const *pos2col_b, uint32_t cols_b,
   const uint32_t *const *row_off, const mo_entry *const *entries, float *post);
 
+/* guide tree: UPGMA5::FixEADistMx + UPGMA5::Run (upgma5.cpp:504-519,87-330); returns -1 if an EA is outside [0,1] */
+int mo_upgma(uint32_t n, const float *ea, int linkage, uint32_t *left, uint32_t *right, float *llen, float *rlen);
+
 #ifdef __cplusplus
 }
 #endif

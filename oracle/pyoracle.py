@@ -161,6 +161,15 @@ class Oracle:
 			res["entries"] = ents
 		return res
 
+	def upgma(self, n, ea, linkage=4):
+		"""-> (left[n-1], right[n-1], left_len, right_len); ea: N(N-1)/2 EA values, row-major i<j"""
+		ea = np.ascontiguousarray(ea, np.float32)
+		L, R = np.empty(n - 1, np.uint32), np.empty(n - 1, np.uint32)
+		LL, RL = np.empty(n - 1, np.float32), np.empty(n - 1, np.float32)
+		rc = self.lib.mo_upgma(n, _p(ea, f32p), linkage, _p(L, u32p), _p(R, u32p), _p(LL, f32p), _p(RL, f32p))
+		assert rc == 0, "EA outside [0,1]"
+		return L, R, LL, RL
+
 	def conspair(self, lens, x, y, row_off, entries):
 		"""row_off/entries: lists indexed by pair index (all pairs). -> updated entries of pair (x,y)"""
 		n = len(lens)
@@ -265,6 +274,13 @@ class Ref:
 		buf = C.create_string_buffer(LX + LY + 1)
 		s = self.lib.ref_calcaln(_p(post, f32p), LX, LY, buf)
 		return float(s), buf.value.decode()
+
+	def upgma(self, n, ea, linkage=4):
+		ea = np.ascontiguousarray(ea, np.float32)
+		L, R = np.empty(n - 1, np.uint32), np.empty(n - 1, np.uint32)
+		LL, RL = np.empty(n - 1, np.float32), np.empty(n - 1, np.float32)
+		self.lib.ref_upgma(n, _p(ea, f32p), linkage, _p(L, u32p), _p(R, u32p), _p(LL, f32p), _p(RL, f32p))
+		return L, R, LL, RL
 
 	def mpc(self, seqs):
 		return RefMPC(self, seqs)

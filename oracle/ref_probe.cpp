@@ -358,4 +358,38 @@ float ref_mpc_alignalns(void *h, int n1, const int *idx1, const char *const *row
 	return Score;
 	}
 
+// MPCFlat::CalcGuideTree's numeric part (mpcflat.cpp:191-194): UPGMA5::Init + FixEADistMx + Run,
+// children / branch lengths read back from the Tree it creates.  ea: N(N-1)/2, row-major i<j.
+int ref_upgma(uint n, const float *ea, int linkage, uint *Left, uint *Right, float *LLen, float *RLen)
+	{
+	vector<string> Labels;
+	vector<vector<float> > DistMx(n, vector<float>(n, 0));
+	uint p = 0;
+	for (uint i = 0; i < n; ++i)
+		{
+		char tmp[32];
+		snprintf(tmp, sizeof tmp, "s%u", i);
+		Labels.push_back(tmp);
+		for (uint j = i + 1; j < n; ++j, ++p)
+			{
+			DistMx[i][j] = ea[p];
+			DistMx[j][i] = ea[p];
+			}
+		}
+	UPGMA5 U;
+	U.Init(Labels, DistMx);
+	U.FixEADistMx();
+	Tree T;
+	U.Run((LINKAGE) linkage, T);
+	for (uint k = 0; k + 1 < n; ++k)
+		{
+		const uint Node = n + k;
+		Left[k] = T.GetLeft(Node);
+		Right[k] = T.GetRight(Node);
+		LLen[k] = (float) T.GetEdgeLength(Node, Left[k]);
+		RLen[k] = (float) T.GetEdgeLength(Node, Right[k]);
+		}
+	return 0;
+	}
+
 } // extern "C"

@@ -105,3 +105,17 @@ def test_random_small_pairs_bitexact(ref, oracle):
 		assert (o1 == o2).all() and e1.tobytes() == e2.tobytes()
 		assert oracle.alnscore(p) == ref.alnscore(p)
 		assert oracle.calcaln(p) == ref.calcaln(p)
+
+
+def test_upgma_oracle_vs_reference(oracle, ref):
+	"""guide tree: the C restatement of UPGMA5::FixEADistMx + Run against the compiled reference, every
+	linkage, random and tie-heavy EA matrices (ties exercise the scan-order and nearest-neighbour quirks)"""
+	rng = np.random.default_rng(11)
+	for trial in range(120):
+		n = int(rng.integers(2, 48))
+		npair = n*(n - 1)//2
+		ea = (rng.integers(0, 5, npair).astype(np.float32)/4) if trial % 3 == 0 else rng.random(npair).astype(np.float32)
+		for link in (1, 2, 3, 4):
+			a, b = oracle.upgma(n, ea, link), ref.upgma(n, ea, link)
+			for x, y in zip(a, b):
+				assert x.tobytes() == y.tobytes(), (trial, n, link)
