@@ -4,14 +4,21 @@
 //   PProg::GetPostPairsAlignedFlat  (getpostpairsalignedflat.cpp:5-98)  -> one mb200_posteriors batch
 //   CalcEADistMx                    (eadistmx.cpp:7-70)                 -> one mb200_posteriors batch
 //   AlignPairFlat_SparsePost / AlignPairFlat (alignpairflat.cpp:3-31)   -> 1-pair batch (+ mb200_align_pairs)
-// Sequences are resolved through the reference's own global label registry
-// (GetGlobalInputSeqByLabel, globalinputms.cpp:125-143) and handed to the library by index.
+//   UClust::Search                  (uclust.cpp:26-57)                  -> ONE batch over all top candidates of a query,
+//                                                                          then the reference's first-accept rule in order
+//   EACluster::GetBestCentroid      (eacluster.cpp:93-143)              -> batches of 32 candidates, the reference's
+//                                                                          accept / early-out rule applied in candidate order
+// Sequences are resolved through the reference's own global label registry (globalinputms.cpp): the
+// whole registry is uploaded ONCE (and again only when it grows or is replaced) and pairs are handed to
+// the library as registry indexes (GSI), so a call moves no sequence data.
 // A context of its own is used so that an MPCFlat store (mpcflat_b200_shim.cpp) is never disturbed;
-// the per-pair entry points are serialised by a mutex (UClust/EACluster call them from OpenMP loops).
+// the entry points are serialised by a mutex (the reference calls some of them from OpenMP loops).
 #include "muscle.h"
 #include "pprog.h"
 #include "pairhmm.h"
 #include "mega.h"
+#include "uclust.h"
+#include "eacluster.h"
 #include "../include/muscle_b200.h"
 #include <mutex>
 #include <unordered_map>
@@ -42,46 +49,73 @@ static void EnsurePairCtx()
 		if (rc != MB200_OK)
 			Die("libmuscle_b200 mb200_create failed (%d): %s", rc, mb200_last_error(0));
 		}
-	CheckP(mb200_set_hmm(g_PairCtx, PairHMM::m_StartScore, &PairHMM::m_TransScore[0][0],
-	  PairHMM::m_InsScore, &PairHMM::m_MatchScore[0][0], MIN_SPARSE_SCORE), "mb200_set_hmm");
+	// the PairHMM tables are process-global statics that can be rewritten between replicates
+	// (align.cpp:30-40): upload them when they differ from what the device holds
+	static vector<float> Cached;
+	vector<float> Now;
+	Now.insert(Now.end(), PairHMM::m_StartScore, PairHMM::m_StartScore + HMMSTATE_COUNT);
+	Now.insert(Now.end(), &PairHMM::m_TransScore[0][0], &PairHMM::m_TransScore[0][0] + HMMSTATE_COUNT*HMMSTATE_COUNT);
+	Now.insert(Now.end(), PairHMM::m_InsScore, PairHMM::m_InsScore + 256);
+	Now.insert(Now.end(), &PairHMM::m_MatchScore[0][0], &PairHMM::m_MatchScore[0][0] + 256*256);
+	if (Now.size() != Cached.size() || memcmp(Now.data(), Cached.data(), Now.size()*sizeof(float)) != 0)
+		{
+		CheckP(mb200_set_hmm(g_PairCtx, PairHMM::m_StartScore, &PairHMM::m_TransScore[0][0],
+		  PairHMM::m_InsScore, &PairHMM::m_MatchScore[0][0], MIN_SPARSE_SCORE), "mb200_set_hmm");
+		Cached.swap(Now);
+		}
 	}
 
-// Upload the distinct sequences named by the two label lists and run the posterior stage on the
-// pair list.  EAs[k] = what CalcAlnFlat(Post)/min(L1,L2) gives in the reference (the max-sum DP
-// value of CalcAlnFlat and CalcAlnScoreFlat is the same number).
+// The registry of input sequences (globalinputms.cpp:60-110) lives on the device as a whole; it is
+// uploaded again only when it grew (AddGlobalTmpSeq: consensus sequences) or was replaced.
+static uint g_UpCount = 0;
+static const void *g_UpFirst = 0, *g_UpLast = 0;
+static void EnsureGlobalSeqs()
+	{
+	const uint Count = GetGSICount();
+	asserta(Count > 0);
+	const void *First = GetSequenceByGSI(0);
+	const void *Last = GetSequenceByGSI(Count - 1);
+	if (Count == g_UpCount && First == g_UpFirst && Last == g_UpLast)
+		return;
+	vector<byte> Bytes;
+	vector<uint64_t> Offsets(1, 0);
+	for (uint GSI = 0; GSI < Count; ++GSI)
+		{
+		const Sequence *Seq = GetSequenceByGSI(GSI);
+		const byte *B = Seq->GetBytePtr();
+		Bytes.insert(Bytes.end(), B, B + Seq->GetLength());
+		Offsets.push_back(Bytes.size());
+		}
+	CheckP(mb200_set_seqs(g_PairCtx, Count, Bytes.data(), Offsets.data()), "mb200_set_seqs");
+	g_UpCount = Count; g_UpFirst = First; g_UpLast = Last;
+	}
+
+// Run the posterior stage on a pair list given by labels.  EAs[k] = what CalcAlnFlat(Post)/min(L1,L2)
+// gives in the reference (the max-sum DP value of CalcAlnFlat and CalcAlnScoreFlat is the same number).
 static void RunPairList(const vector<string> &Labels1, const vector<string> &Labels2, vector<float> &EAs)
 	{
 	const uint PairCount = SIZE(Labels1);
 	asserta(SIZE(Labels2) == PairCount && PairCount > 0);
-	unordered_map<string, uint> LabelToId;
-	vector<byte> Bytes;
-	vector<uint64_t> Offsets(1, 0);
+	EnsureGlobalSeqs();
 	vector<uint> PX(PairCount), PY(PairCount);
 	for (uint k = 0; k < PairCount; ++k)
 		{
-		for (int side = 0; side < 2; ++side)
-			{
-			const string &Label = side == 0 ? Labels1[k] : Labels2[k];
-			unordered_map<string, uint>::const_iterator it = LabelToId.find(Label);
-			uint Id;
-			if (it == LabelToId.end())
-				{
-				Id = SIZE(LabelToId);
-				LabelToId[Label] = Id;
-				const Sequence &Seq = GetGlobalInputSeqByLabel(Label);
-				const byte *B = Seq.GetBytePtr();
-				Bytes.insert(Bytes.end(), B, B + Seq.GetLength());
-				Offsets.push_back(Bytes.size());
-				}
-			else
-				Id = it->second;
-			(side == 0 ? PX : PY)[k] = Id;
-			}
+		PX[k] = GetGSIByLabel(Labels1[k]);
+		PY[k] = GetGSIByLabel(Labels2[k]);
 		}
-	CheckP(mb200_set_seqs(g_PairCtx, SIZE(LabelToId), Bytes.data(), Offsets.data()), "mb200_set_seqs");
 	EAs.resize(PairCount);
 	CheckP(mb200_posteriors(g_PairCtx, PairCount, PX.data(), PY.data(), MB200_POST_DEFAULT, EAs.data()),
 	  "mb200_posteriors");
+	}
+
+// decoding path of one pair of the current store (CalcAlnFlat + traceback on the device)
+static void StorePairPath(uint StorePair, uint LX, uint LY, string &Path)
+	{
+	uint64_t PathOff[2] = { 0, uint64_t(LX) + LY + 1 };
+	vector<char> PathBuf(LX + LY + 2);
+	float Score = 0;
+	CheckP(mb200_align_pairs(g_PairCtx, 1, &StorePair, PathBuf.data(), PathOff, &Score), "mb200_align_pairs");
+	Path = string(PathBuf.data());
 	}
 
 // fill host MySparseMx objects (MySparseMx::FromPost layout) for store pairs [0,PairCount)
@@ -213,13 +247,10 @@ float AlignPairFlat_SparsePost(const string &Label1, const string &Label2,
 	RunPairList(L1, L2, EAs);
 	const uint LX = GetSeqLengthByGlobalLabel(Label1);
 	const uint LY = GetSeqLengthByGlobalLabel(Label2);
-	// the decoding path: max-sum DP + traceback on the stored sparse posterior
-	uint StorePair = 0;
-	uint64_t PathOff[2] = { 0, uint64_t(LX) + LY + 1 };
-	vector<char> PathBuf(LX + LY + 2);
-	float Score = 0;
-	CheckP(mb200_align_pairs(g_PairCtx, 1, &StorePair, PathBuf.data(), PathOff, &Score), "mb200_align_pairs");
-	Path = string(PathBuf.data());
+	// the decoding path: max-sum DP + traceback on the stored sparse posterior.  The reference decodes
+	// from the dense thresholded matrix (alignpairflat.cpp:8-13); the two hold the same cells because no
+	// score passes the log cut and fails the probability cut (tests/test_threshold_band_cpu.py).
+	StorePairPath(0, LX, LY, Path);
 	if (SparsePost != 0)
 		{
 		SparsePost->m_LX = LX;
@@ -233,4 +264,108 @@ float AlignPairFlat_SparsePost(const string &Label1, const string &Label2,
 float AlignPairFlat(const string &Label1, const string &Label2, string &Path)
 	{
 	return AlignPairFlat_SparsePost(Label1, Label2, Path, 0);
+	}
+
+
+// uclust.cpp:26-57.  The reference aligns the query to its top word-count candidates ONE AT A TIME and
+// stops at the first with EA >= MinEA; the candidates are known up front and the alignments are pure
+// functions, so all of them run as one device batch and the first-accept rule is applied afterwards in
+// the same order -- same centroid, same path.
+uint UClust::Search(uint SeqIndex, string &Path)
+	{
+	const Sequence *Seq = m_InputSeqs->GetSequence(SeqIndex);
+	const byte *ByteSeq = Seq->GetBytePtr();
+	const uint L = Seq->GetLength();
+
+	vector<uint> TopSeqIndexes;
+	vector<uint> TopWordCounts;
+	m_US.SearchSeq(ByteSeq, L, TopSeqIndexes, TopWordCounts);
+	uint TopCount = SIZE(TopSeqIndexes);
+	asserta(SIZE(TopWordCounts) == TopCount);
+	if (TopCount == 0)
+		return UINT_MAX;
+	if (TopCount > MAX_REJECTS)
+		TopCount = MAX_REJECTS;
+
+	std::lock_guard<std::mutex> Guard(g_PairMutex);
+	EnsurePairCtx();
+	vector<string> L1, L2;
+	for (uint TopIndex = 0; TopIndex < TopCount; ++TopIndex)
+		{
+		L1.push_back(Seq->m_Label);
+		L2.push_back(m_InputSeqs->GetSequence(TopSeqIndexes[TopIndex])->m_Label);
+		}
+	vector<float> EAs;
+	RunPairList(L1, L2, EAs);
+	Path.clear();
+	for (uint TopIndex = 0; TopIndex < TopCount; ++TopIndex)
+		if (EAs[TopIndex] >= m_MinEA)
+			{
+			const uint TopSeqIndex = TopSeqIndexes[TopIndex];
+			StorePairPath(TopIndex, L, m_InputSeqs->GetSequence(TopSeqIndex)->GetLength(), Path);
+			return TopSeqIndex;
+			}
+	return UINT_MAX;
+	}
+
+// eacluster.cpp:93-143.  The reference evaluates the candidates in an OpenMP loop with a shared early-out
+// flag (its result depends on thread timing); here they are evaluated in device batches of 32 and the
+// accept / early-out rule is applied in candidate order, i.e. exactly the reference's `-threads 1` result.
+uint EACluster::GetBestCentroid(uint SeqIndex, float MinEA, float &BestEA)
+	{
+	uint CentroidCount = SIZE(m_CentroidSeqIndexes);
+	if (CentroidCount == 0)
+		return UINT_MAX;
+
+	uint L;
+	const byte *ByteSeq = m_InputSeqs->GetByteSeq(SeqIndex, L);
+
+	vector<uint> TopSeqIndexes;
+	vector<uint> TopWordCounts;
+	m_US.SearchSeq(ByteSeq, L, TopSeqIndexes, TopWordCounts);
+	const uint TopCount = SIZE(TopSeqIndexes);
+	asserta(SIZE(TopWordCounts) == TopCount);
+	if (TopCount == 0)
+		return UINT_MAX;
+
+	std::lock_guard<std::mutex> Guard(g_PairMutex);
+	EnsurePairCtx();
+	BestEA = 0;
+	uint BestCentroidIndex = UINT_MAX;
+	bool Done = false;
+	const string Label = m_InputSeqs->GetLabel(SeqIndex);
+	const uint CHUNK = 32;
+	for (uint Top0 = 0; Top0 < TopCount && !Done; Top0 += CHUNK)
+		{
+		const uint n = min(CHUNK, TopCount - Top0);
+		vector<string> L1(n, Label), L2;
+		for (uint k = 0; k < n; ++k)
+			L2.push_back(m_InputSeqs->GetLabel(TopSeqIndexes[Top0 + k]));
+		vector<float> EAs;
+		RunPairList(L1, L2, EAs);
+		for (uint k = 0; k < n && !Done; ++k)
+			{
+			const int TopIndex = int(Top0 + k);
+			const uint TopSeqIndex = TopSeqIndexes[TopIndex];
+			const float EA = EAs[k];
+			if (EA > MinEA && EA > BestEA)
+				{
+				BestEA = EA;
+				asserta(TopSeqIndex < SIZE(m_SeqIndexToCentroidIndex));
+				uint CentroidIndex = m_SeqIndexToCentroidIndex[TopSeqIndex];
+				asserta(CentroidIndex < CentroidCount);
+				BestCentroidIndex = CentroidIndex;
+				}
+			if (BestEA >= MinEA)
+				{
+				if (BestEA > 0.9)
+					Done = true;
+				if (BestEA - EA > 0.3)
+					Done = true;
+				}
+			if (BestEA < MinEA - 0.3 && TopIndex > 20)
+				Done = true;
+			}
+		}
+	return BestCentroidIndex;
 	}
