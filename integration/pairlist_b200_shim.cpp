@@ -65,29 +65,63 @@ static void EnsurePairCtx()
 		}
 	}
 
-// The registry of input sequences (globalinputms.cpp:60-110) lives on the device as a whole; it is
-// uploaded again only when it grew (AddGlobalTmpSeq: consensus sequences) or was replaced.
-static uint g_UpCount = 0;
-static const void *g_UpFirst = 0, *g_UpLast = 0;
-static void EnsureGlobalSeqs()
+// The sequences the pair lists name live on the device persistently: the input registry
+// (globalinputms.cpp:68-93) is uploaded as a whole the first time, temporary sequences (consensus
+// sequences registered with AddGlobalTmpSeq, :60-66, known by label only) are appended when first seen,
+// and everything is uploaded again only when something was appended or a label now names other bytes.
+struct DevSeq { uint Id; const Sequence *Ptr; uint Length; };
+static unordered_map<string, DevSeq> g_LabelToDev;
+static vector<byte> g_DevBytes;
+static vector<uint64_t> g_DevOffsets(1, 0);
+static bool g_DevDirty = false;
+static const void *g_RegistryFirst = 0;
+
+static uint AppendDevSeq(const string &Label, const Sequence *Seq)
+	{
+	const byte *B = Seq->GetBytePtr();
+	const uint L = Seq->GetLength();
+	DevSeq D;
+	D.Id = SIZE(g_DevOffsets) - 1;
+	D.Ptr = Seq;
+	D.Length = L;
+	g_DevBytes.insert(g_DevBytes.end(), B, B + L);
+	g_DevOffsets.push_back(g_DevBytes.size());
+	g_LabelToDev[Label] = D;
+	g_DevDirty = true;
+	return D.Id;
+	}
+
+static uint DevIdOfLabel(const string &Label)
+	{
+	const Sequence *Seq = &GetGlobalInputSeqByLabel(Label);          // Die()s on an unknown label, like the reference
+	unordered_map<string, DevSeq>::const_iterator it = g_LabelToDev.find(Label);
+	if (it != g_LabelToDev.end())
+		{
+		const DevSeq &D = it->second;
+		if (D.Ptr == Seq && D.Length == Seq->GetLength() &&
+		  memcmp(g_DevBytes.data() + g_DevOffsets[D.Id], Seq->GetBytePtr(), D.Length) == 0)
+			return D.Id;
+		}
+	return AppendDevSeq(Label, Seq);                                  // new, or the label now names another sequence
+	}
+
+static void EnsureRegistry()
 	{
 	const uint Count = GetGSICount();
 	asserta(Count > 0);
 	const void *First = GetSequenceByGSI(0);
-	const void *Last = GetSequenceByGSI(Count - 1);
-	if (Count == g_UpCount && First == g_UpFirst && Last == g_UpLast)
+	if (First == g_RegistryFirst)
 		return;
-	vector<byte> Bytes;
-	vector<uint64_t> Offsets(1, 0);
+	// first use, or the registry was replaced: start over
+	g_LabelToDev.clear();
+	g_DevBytes.clear();
+	g_DevOffsets.assign(1, 0);
 	for (uint GSI = 0; GSI < Count; ++GSI)
 		{
 		const Sequence *Seq = GetSequenceByGSI(GSI);
-		const byte *B = Seq->GetBytePtr();
-		Bytes.insert(Bytes.end(), B, B + Seq->GetLength());
-		Offsets.push_back(Bytes.size());
+		AppendDevSeq(Seq->m_Label, Seq);
 		}
-	CheckP(mb200_set_seqs(g_PairCtx, Count, Bytes.data(), Offsets.data()), "mb200_set_seqs");
-	g_UpCount = Count; g_UpFirst = First; g_UpLast = Last;
+	g_RegistryFirst = First;
 	}
 
 // Run the posterior stage on a pair list given by labels.  EAs[k] = what CalcAlnFlat(Post)/min(L1,L2)
@@ -96,12 +130,17 @@ static void RunPairList(const vector<string> &Labels1, const vector<string> &Lab
 	{
 	const uint PairCount = SIZE(Labels1);
 	asserta(SIZE(Labels2) == PairCount && PairCount > 0);
-	EnsureGlobalSeqs();
+	EnsureRegistry();
 	vector<uint> PX(PairCount), PY(PairCount);
 	for (uint k = 0; k < PairCount; ++k)
 		{
-		PX[k] = GetGSIByLabel(Labels1[k]);
-		PY[k] = GetGSIByLabel(Labels2[k]);
+		PX[k] = DevIdOfLabel(Labels1[k]);
+		PY[k] = DevIdOfLabel(Labels2[k]);
+		}
+	if (g_DevDirty)
+		{
+		CheckP(mb200_set_seqs(g_PairCtx, SIZE(g_DevOffsets) - 1, g_DevBytes.data(), g_DevOffsets.data()), "mb200_set_seqs");
+		g_DevDirty = false;
 		}
 	EAs.resize(PairCount);
 	CheckP(mb200_posteriors(g_PairCtx, PairCount, PX.data(), PY.data(), MB200_POST_DEFAULT, EAs.data()),
