@@ -63,6 +63,20 @@ int mb200_set_hmm(mb200_ctx *ctx, const float start[5], const float trans[25],
  * Invalidates any stored posteriors. */
 int mb200_set_seqs(mb200_ctx *ctx, uint32_t nseq, const uint8_t *bytes, const uint64_t *offsets);
 
+/* Mega / Muscle-3D feature profiles instead of residue bytes: the emission
+ * side of Mega::CalcFwdFlat_mega / CalcBwdFlat_mega (fwdflat_mega.cpp:14, bwdflat_mega.cpp), i.e. what
+ * CalcPost switches to when a .mega input is loaded (calcpost.cpp:14-22).  A position is a vector of
+ * nfeat <= 8 feature letters (Mega::m_Profiles, mega.h:25): letters[(offsets[s]+i)*nfeat + f].
+ * alpha[f] = alphabet size (Mega::m_AlphaSizes), weights[f] = Mega::m_Weights, logprobs = the vectors
+ * Mega::m_LogProbsVec[f] back to back, logprobmx = the matrices Mega::m_LogProbMxVec[f] (row-major)
+ * back to back.  Match emission = sum_f logprobmx_f[a_f][b_f]*w_f, insert emission = sum_f
+ * logprobs_f[a_f]*w_f, both accumulated from 0 in feature order with separate fp32 multiply and add
+ * (Mega::GetMatchScore / GetInsScore, mega.cpp:273-359).  Transitions and the sparsification cut still
+ * come from mb200_set_hmm.  Replaces mb200_set_seqs (either call selects the emission mode). */
+int mb200_set_seqs_mega(mb200_ctx *ctx, uint32_t nseq, const uint8_t *letters, const uint64_t *offsets,
+                        uint32_t nfeat, const uint32_t *alpha, const float *weights,
+                        const float *logprobs, const float *logprobmx);
+
 /* ---- posterior stage --------------------------------------------------------------------- */
 /* Replaces the OpenMP loop MPCFlat::CalcPosteriors (mpcflat.cpp:214-252) and, per pair,
  * MPCFlat::CalcPosterior (calcposteriorflat.cpp:45-92) = CalcPost (calcpost.cpp:4: CalcFwdFlat
@@ -228,6 +242,9 @@ mb200_ctx  *mb200_group_ctx(mb200_group *g, int rank);
 int mb200_group_set_hmm(mb200_group *g, const float start[5], const float trans[25],
                         const float ins[256], const float match[65536], float min_sparse_score);
 int mb200_group_set_seqs(mb200_group *g, uint32_t nseq, const uint8_t *bytes, const uint64_t *offsets);
+int mb200_group_set_seqs_mega(mb200_group *g, uint32_t nseq, const uint8_t *letters, const uint64_t *offsets,
+                              uint32_t nfeat, const uint32_t *alpha, const float *weights,
+                              const float *logprobs, const float *logprobmx);
 int mb200_group_posteriors_allpairs(mb200_group *g, float *ea_out);   /* ea_out[N(N-1)/2], may be NULL */
 int mb200_group_consistency_iter(mb200_group *g);
 typedef struct

@@ -15,8 +15,9 @@
 //                                                      -> one mb200_msa_join per bipartition (same rand() stream)
 // Everything else (FASTA I/O, dereplication, Tree object and join order, sorting, MSA output) is the
 // reference's own code, untouched.  Errors keep the reference convention: Die() -> message +
-// exit(1) (myutils.cpp:883).  There is no CPU fallback: inputs the engine does not implement (Mega
-// feature profiles) stop with a message instead of silently running something else.
+// exit(1) (myutils.cpp:883).  There is no CPU fallback.  A .mega input (Muscle-3D feature profiles)
+// selects the engine's Mega emission mode for `-align`; the pair-list callers of -super7
+// (pairlist_b200_shim.cpp) do not implement it and stop with a message instead of computing something else.
 #include "muscle.h"
 #include "mpcflat.h"
 #include "pairhmm.h"
@@ -61,13 +62,6 @@ static void CheckG(int rc, const char *What)
 		Die("libmuscle_b200 %s failed (%d): %s", What, rc, mb200_group_last_error(g_Group));
 	}
 
-static void NoMega()
-	{
-	if (Mega::m_Loaded)
-		Die("muscle_b200: Mega feature profiles (-mega / .mega input) are not implemented by the B200 engine; "
-		  "use the CPU build of muscle for this input");
-	}
-
 static void EnsureGroup()
 	{
 	if (g_Group != 0)
@@ -93,7 +87,6 @@ static void EnsureGroup()
 // the whole posterior stage of one MPCFlat object on the device(s)
 static void RunPosteriors(MPCFlat &M)
 	{
-	NoMega();
 	EnsureGroup();
 	const uint SeqCount = M.GetSeqCount();
 	const uint PairCount = SIZE(M.m_Pairs);
@@ -107,14 +100,55 @@ static void RunPosteriors(MPCFlat &M)
 	vector<byte> Bytes;
 	vector<uint64_t> Offsets;
 	Offsets.push_back(0);
-	for (uint i = 0; i < SeqCount; ++i)
+	if (Mega::m_Loaded)
 		{
-		const byte *Seq = M.GetBytePtr(i);
-		const uint L = M.GetSeqLength(i);
-		Bytes.insert(Bytes.end(), Seq, Seq + L);
-		Offsets.push_back(Bytes.size());
+		// calcpost.cpp:14-22: with a .mega input the emissions come from the feature profiles
+		// (Mega::CalcFwdFlat_mega / CalcBwdFlat_mega); hand the model the host derived and the profiles
+		// of this object's sequences (looked up by label, like CalcPost does) to the engine
+		const uint F = Mega::GetFeatureCount();
+		vector<uint> Alpha(F);
+		vector<float> Weights(F), LogProbs, LogProbMx;
+		for (uint f = 0; f < F; ++f)
+			{
+			const uint A = Mega::GetAlphaSize(f);
+			Alpha[f] = A;
+			Weights[f] = Mega::GetWeight(f);
+			asserta(SIZE(Mega::m_LogProbsVec[f]) == A && SIZE(Mega::m_LogProbMxVec[f]) == A);
+			LogProbs.insert(LogProbs.end(), Mega::m_LogProbsVec[f].begin(), Mega::m_LogProbsVec[f].end());
+			for (uint x = 0; x < A; ++x)
+				{
+				asserta(SIZE(Mega::m_LogProbMxVec[f][x]) == A);
+				LogProbMx.insert(LogProbMx.end(), Mega::m_LogProbMxVec[f][x].begin(), Mega::m_LogProbMxVec[f][x].end());
+				}
+			}
+		uint64_t Pos = 0;
+		for (uint i = 0; i < SeqCount; ++i)
+			{
+			const vector<vector<byte> > &Profile = *Mega::GetProfileByLabel(string(M.GetLabel(i)));
+			const uint L = M.GetSeqLength(i);
+			asserta(SIZE(Profile) == L);
+			for (uint k = 0; k < L; ++k)
+				{
+				asserta(SIZE(Profile[k]) == F);
+				Bytes.insert(Bytes.end(), Profile[k].begin(), Profile[k].end());
+				}
+			Pos += L;
+			Offsets.push_back(Pos);
+			}
+		CheckG(mb200_group_set_seqs_mega(g_Group, SeqCount, Bytes.data(), Offsets.data(), F, Alpha.data(), Weights.data(),
+		  LogProbs.data(), LogProbMx.data()), "mb200_group_set_seqs_mega");
 		}
-	CheckG(mb200_group_set_seqs(g_Group, SeqCount, Bytes.data(), Offsets.data()), "mb200_group_set_seqs");
+	else
+		{
+		for (uint i = 0; i < SeqCount; ++i)
+			{
+			const byte *Seq = M.GetBytePtr(i);
+			const uint L = M.GetSeqLength(i);
+			Bytes.insert(Bytes.end(), Seq, Seq + L);
+			Offsets.push_back(Bytes.size());
+			}
+		CheckG(mb200_group_set_seqs(g_Group, SeqCount, Bytes.data(), Offsets.data()), "mb200_group_set_seqs");
+		}
 
 	vector<float> EAs(PairCount);
 	CheckG(mb200_group_posteriors_allpairs(g_Group, EAs.data()), "mb200_group_posteriors_allpairs");

@@ -157,9 +157,11 @@ __device__ __forceinline__ float mb_expf_glibc(float x)
 struct PostParams
 	{
 	MbHmm h;
-	const float   *matchT;          // K*KS
-	const float   *insT;            // K
-	const uint8_t *codes;           // residue classes, all sequences back to back
+	const float   *matchT;          // K*KS                       | MEGA: concatenated pre-multiplied feature pair tables
+	const float   *insT;            // K                          | MEGA: insert emission of every position
+	const uint8_t *codes;           // residue classes, all sequences back to back | MEGA: 8 feature letters per position
+	uint32_t mega_nf, mega_tsize;   // MEGA: features (<= 8), floats in the table
+	uint32_t mega_base[8], mega_alpha[8];   // MEGA: offset and alphabet size of each feature's table
 	const uint64_t *seqoff;
 	const uint32_t *seqlen;
 	const uint32_t *px, *py;        // store pair -> sequence ids

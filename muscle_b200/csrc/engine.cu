@@ -118,7 +118,7 @@ void mb200_destroy(mb200_ctx *ctx)
 	  &ctx->d_ea, &ctx->d_dbg, &ctx->d_pack_off, &ctx->d_pack_ent, &ctx->d_entries2,
 	  &ctx->d_tr_rowoff, &ctx->d_tr_rowbase, &ctx->d_tr_entries, &ctx->d_tr_entbase, &ctx->d_tr_perm,
 	  &ctx->d_tmp, &ctx->d_tmp2, &ctx->d_mk_hdr, &ctx->d_mk_words, &ctx->d_tr_mk_hdr, &ctx->d_tr_mk_words,
-	  &ctx->d_relax_order, &ctx->d_p2c, &ctx->d_join, &ctx->d_stage };
+	  &ctx->d_relax_order, &ctx->d_p2c, &ctx->d_join, &ctx->d_stage, &ctx->d_megaT, &ctx->d_insP };
 	if (ctx->h_pinned)
 		cudaFreeHost(ctx->h_pinned);
 	for (DevBuf *b : bufs)
@@ -237,6 +237,8 @@ int mb200_set_hmm(mb200_ctx *ctx, const float start[5], const float trans[25], c
 
 static int recode_seqs(mb200_ctx *ctx)
 	{
+	if (ctx->mega)
+		return MB200_OK;                   // feature letters are not residue classes: nothing depends on the tables
 	std::vector<uint8_t> codes(ctx->h_bytes.size());
 	for (size_t k = 0; k < codes.size(); ++k)
 		codes[k] = ctx->byte2class[ctx->h_bytes[k]];
@@ -261,6 +263,7 @@ int mb200_set_seqs(mb200_ctx *ctx, uint32_t nseq, const uint8_t *bytes, const ui
 			return mb_fail(ctx, MB200_EOVERFLOW, "sequence %u too long", i);
 		}
 	ctx->nseq = nseq;
+	ctx->mega = false;
 	ctx->h_off.assign(offsets, offsets + nseq + 1);
 	ctx->h_len.resize(nseq);
 	for (uint32_t i = 0; i < nseq; ++i)
@@ -284,6 +287,97 @@ int mb200_set_seqs(mb200_ctx *ctx, uint32_t nseq, const uint8_t *bytes, const ui
 	if (ctx->have_hmm)
 		return recode_seqs(ctx);
 	CU(cudaStreamSynchronize(ctx->stream));
+	return MB200_OK;
+	}
+
+// Mega (Muscle-3D) feature profiles instead of residue bytes.  Replaces the emission side of
+// Mega::CalcFwdFlat_mega / CalcBwdFlat_mega (fwdflat_mega.cpp:14, bwdflat_mega.cpp): the pair tables
+// are pre-multiplied by the feature weights and the insert emission of every position is summed in
+// feature order, with the same fp32 operations as Mega::GetMatchScore / GetInsScore (mega.cpp:273-359).
+int mb200_set_seqs_mega(mb200_ctx *ctx, uint32_t nseq, const uint8_t *letters, const uint64_t *offsets,
+  uint32_t nfeat, const uint32_t *alpha, const float *weights, const float *logprobs, const float *logprobmx)
+	{
+	if (!ctx || !letters || !offsets || !alpha || !weights || !logprobs || !logprobmx || nseq == 0)
+		return mb_fail(ctx, MB200_EINVAL, "mb200_set_seqs_mega: bad argument");
+	if (nfeat == 0 || nfeat > 8)
+		return mb_fail(ctx, MB200_EALPHABET, "mb200_set_seqs_mega: %u features, the kernel handles 1..8", nfeat);
+	cudaSetDevice(ctx->device);
+	uint32_t tsize = 0, lsize = 0, base[8] = {}, lbase[8] = {};
+	for (uint32_t f = 0; f < nfeat; ++f)
+		{
+		if (alpha[f] == 0 || alpha[f] > 256)
+			return mb_fail(ctx, MB200_EALPHABET, "mb200_set_seqs_mega: feature %u has alphabet size %u", f, alpha[f]);
+		base[f] = tsize; lbase[f] = lsize;
+		tsize += alpha[f]*alpha[f];
+		lsize += alpha[f];
+		}
+	if (tsize > 12*1024)
+		return mb_fail(ctx, MB200_EALPHABET, "mb200_set_seqs_mega: pair tables of %u floats do not fit the kernel's shared memory", tsize);
+	for (uint32_t i = 0; i < nseq; ++i)
+		{
+		if (offsets[i + 1] <= offsets[i])
+			return mb_fail(ctx, MB200_EINVAL, "profile %u is empty or offsets not increasing", i);
+		if (offsets[i + 1] - offsets[i] > 0x7fffffffull)
+			return mb_fail(ctx, MB200_EOVERFLOW, "profile %u too long", i);
+		}
+	const uint64_t o0 = offsets[0], npos = offsets[nseq] - o0;
+	std::vector<uint8_t> packed(npos*8, 0);
+	std::vector<float> insP(npos);
+	for (uint64_t r = 0; r < npos; ++r)
+		{
+		const uint8_t *col = letters + (o0 + r)*nfeat;
+		float score = 0;
+		for (uint32_t f = 0; f < nfeat; ++f)
+			{
+			if (col[f] >= alpha[f])
+				return mb_fail(ctx, MB200_EINVAL, "profile position %llu: letter %u of feature %u outside its alphabet",
+				  (unsigned long long) r, col[f], f);
+			packed[r*8 + f] = col[f];
+			const float term = logprobs[lbase[f] + col[f]]*weights[f];        // mega.cpp:283
+			score += term;
+			}
+		insP[r] = score;
+		}
+	std::vector<float> T(tsize);
+	for (uint32_t f = 0; f < nfeat; ++f)
+		for (uint32_t k = 0; k < alpha[f]*alpha[f]; ++k)
+			T[base[f] + k] = logprobmx[base[f] + k]*weights[f];                 // mega.cpp:355-356
+	ctx->nseq = nseq;
+	ctx->mega = true;
+	ctx->mega_nf = nfeat;
+	ctx->mega_tsize = tsize;
+	for (uint32_t f = 0; f < 8; ++f)
+		{
+		ctx->mega_base[f] = f < nfeat ? base[f] : 0;
+		ctx->mega_alpha[f] = f < nfeat ? alpha[f] : 0;
+		}
+	ctx->h_off.assign(offsets, offsets + nseq + 1);
+	for (auto &o : ctx->h_off)
+		o -= o0;
+	ctx->h_len.resize(nseq);
+	for (uint32_t i = 0; i < nseq; ++i)
+		ctx->h_len[i] = (uint32_t)(offsets[i + 1] - offsets[i]);
+	ctx->h_bytes.clear();
+	ctx->msa_valid = false;
+	ENSURE(ctx->d_seqoff, (nseq + 1)*sizeof(uint64_t));
+	ENSURE(ctx->d_seqlen, nseq*sizeof(uint32_t));
+	ENSURE(ctx->d_codes, packed.size() + 16);
+	ENSURE(ctx->d_insP, insP.size()*sizeof(float) + 16);
+	ENSURE(ctx->d_megaT, T.size()*sizeof(float) + 16);
+	cudaStream_t st = ctx->stream;
+	CU(cudaMemcpyAsync(ctx->d_seqoff.p, ctx->h_off.data(), (nseq + 1)*sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+	CU(cudaMemcpyAsync(ctx->d_seqlen.p, ctx->h_len.data(), nseq*sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+	CU(cudaMemcpyAsync(ctx->d_codes.p, packed.data(), packed.size(), cudaMemcpyHostToDevice, st));
+	CU(cudaMemcpyAsync(ctx->d_insP.p, insP.data(), insP.size()*sizeof(float), cudaMemcpyHostToDevice, st));
+	CU(cudaMemcpyAsync(ctx->d_megaT.p, T.data(), T.size()*sizeof(float), cudaMemcpyHostToDevice, st));
+	CU(cudaStreamSynchronize(st));
+	ctx->stats.h2d_bytes = (nseq + 1)*sizeof(uint64_t) + nseq*sizeof(uint32_t) + packed.size() + insP.size()*4 + T.size()*4;
+	ctx->stats.d2h_bytes = 0;
+	ctx->store_valid = false;
+	ctx->store_allpairs = false;
+	ctx->ea_allpairs = false;
+	ctx->plan_valid = false;
+	ctx->last_used_entries = 0;
 	return MB200_OK;
 	}
 
@@ -415,17 +509,19 @@ static int run_posteriors(mb200_ctx *ctx, float *ea_out, const PostDebug *dbg, i
 			const uint32_t nstrips = (lymax + W - 1)/W;
 			int smem_static = 0, occ = 0;
 			size_t smem;
-			mb_post_sm_dispatch(2, dim3(), 0, ks, nullptr, &smem_static);
-			smem = (size_t) smem_static + (size_t)((ctx->hmm.K*ctx->hmm.KS + 3) & ~3)*sizeof(float)
-			  + (size_t) MB_WARPS_PER_BLOCK*6*C*32*sizeof(float);
-			if (ctx->occ_cache_k != ctx->hmm.K*ctx->hmm.KS)
+			const bool mega = ctx->mega;
+			const int tsize = mega ? (int) ctx->mega_tsize : ctx->hmm.K*ctx->hmm.KS;
+			mb_post_sm_dispatch(mega, 2, dim3(), 0, ks, nullptr, &smem_static);
+			smem = (size_t) smem_static + (size_t)((tsize + 3) & ~3)*sizeof(float)
+			  + (size_t) MB_WARPS_PER_BLOCK*(mega ? 7 : 6)*C*32*sizeof(float);
+			if (ctx->occ_cache_k != tsize*2 + (mega ? 1 : 0))
 				{
 				memset(ctx->occ_cache, 0, sizeof ctx->occ_cache);
-				ctx->occ_cache_k = ctx->hmm.K*ctx->hmm.KS;
+				ctx->occ_cache_k = tsize*2 + (mega ? 1 : 0);
 				}
 			if (ctx->occ_cache[C] == 0)
 				{
-				mb_post_sm_dispatch(1, dim3(), smem, ks, nullptr, &occ);
+				mb_post_sm_dispatch(mega, 1, dim3(), smem, ks, nullptr, &occ);
 				ctx->occ_cache[C] = occ;
 				}
 			occ = ctx->occ_cache[C];
@@ -460,8 +556,11 @@ static int run_posteriors(mb200_ctx *ctx, float *ea_out, const PostDebug *dbg, i
 			if (ctx->d_fm[C].cap + ctx->d_edge[C].cap + ctx->d_rows[C].cap + ctx->d_rowcnt[C].cap != cap_before)
 				free_b = 0;                        // something was (re)allocated: ask again for the next size class
 			P.h = ctx->hmm;
-			P.matchT = (const float *) ctx->d_matchT.p;
-			P.insT = (const float *) ctx->d_insT.p;
+			P.matchT = (const float *)(mega ? ctx->d_megaT.p : ctx->d_matchT.p);
+			P.insT = (const float *)(mega ? ctx->d_insP.p : ctx->d_insT.p);
+			P.mega_nf = ctx->mega_nf; P.mega_tsize = ctx->mega_tsize;
+			memcpy(P.mega_base, ctx->mega_base, sizeof P.mega_base);
+			memcpy(P.mega_alpha, ctx->mega_alpha, sizeof P.mega_alpha);
 			P.codes = (const uint8_t *) ctx->d_codes.p;
 			P.seqoff = (const uint64_t *) ctx->d_seqoff.p;
 			P.seqlen = (const uint32_t *) ctx->d_seqlen.p;
@@ -488,7 +587,7 @@ static int run_posteriors(mb200_ctx *ctx, float *ea_out, const PostDebug *dbg, i
 				P.dbg_fwd = dbg->fwd; P.dbg_bwd = dbg->bwd; P.dbg_post = dbg->post; P.dbg_total = dbg->total;
 				}
 			P.cmax = (uint32_t) C;
-			mb_post_sm_dispatch(0, dim3(nblocks), smem, ks, &P, nullptr);
+			mb_post_sm_dispatch(mega, 0, dim3(nblocks), smem, ks, &P, nullptr);
 			CU(cudaGetLastError());
 			ctx->stats.kernel_launches++;
 			}

@@ -34,6 +34,10 @@ struct mb200_ctx
 	std::vector<uint64_t> h_off;
 	std::vector<uint32_t> h_len;
 	DevBuf d_codes, d_seqoff, d_seqlen;
+	// Mega feature-profile emissions (mb200_set_seqs_mega): d_codes then holds 8 letters per position
+	bool mega = false;
+	uint32_t mega_nf = 0, mega_tsize = 0, mega_base[8] = {}, mega_alpha[8] = {};
+	DevBuf d_megaT, d_insP;
 
 	// the store: sparse posteriors of the listed pairs (replaces MPCFlat::m_SparsePosts1/2)
 	bool store_valid = false;

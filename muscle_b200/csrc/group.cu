@@ -174,6 +174,16 @@ int mb200_group_set_seqs(mb200_group *g, uint32_t nseq, const uint8_t *bytes, co
 	return on_all(g, [&](int r) { return mb200_set_seqs(g->ctx[r], nseq, bytes, offsets); });
 	}
 
+int mb200_group_set_seqs_mega(mb200_group *g, uint32_t nseq, const uint8_t *letters, const uint64_t *offsets,
+  uint32_t nfeat, const uint32_t *alpha, const float *weights, const float *logprobs, const float *logprobmx)
+	{
+	if (!g)
+		return MB200_EINVAL;
+	g->sharded = false;
+	return on_all(g, [&](int r)
+		{ return mb200_set_seqs_mega(g->ctx[r], nseq, letters, offsets, nfeat, alpha, weights, logprobs, logprobmx); });
+	}
+
 // contiguous ranges of the row-major pair list with ~equal DP cells (sum of LX*LY) per device
 static void shard_pairs(const std::vector<uint32_t> &len, int ndev, std::vector<uint32_t> &lo, std::vector<uint32_t> &hi)
 	{

@@ -29,10 +29,19 @@
 // row/column of Backward, bwdflat3.cpp:132-176) fall out of the general cell update when the
 // out-of-range neighbours are LOG_ZERO.  The only injected values are the start scores at Forward
 // (0,0) and the end scores at Backward (LX,LY) (bwdflat3.cpp:53-61).
+//
+// Emissions.  Plain mode: residue classes index a K x K match table and a K-entry insert table
+// (PairHMM::m_MatchScore / m_InsScore, pairhmm.h:26-29).  MEGA mode (Muscle-3D feature profiles,
+// Mega::CalcFwdFlat_mega / CalcBwdFlat_mega, fwdflat_mega.cpp:14, bwdflat_mega.cpp): a position is a
+// vector of <= 8 feature letters; the match emission of a cell is the sum over features of
+// LogProbMx_f[a_f][b_f]*w_f accumulated from 0 in feature order (Mega::GetMatchScore,
+// mega.cpp:340-359) -- the products are formed once on the host (same fp32 multiply), the kernel adds
+// them in order -- and the insert emission is a per-position value precomputed the same way
+// (Mega::GetInsScore, mega.cpp:273-286).  Same recurrences, same kernel, one template flag.
 #pragma once
 #include "common.cuh"
 
-#define MB_SM_ARRAYS 6            // S/old, M, IX, JX, ycode, eY
+#define MB_SM_ARRAYS 6            // S/old, M, IX, JX, ycode, eY  (+1 in MEGA mode: second word of feature letters)
 #ifndef MB_SM_BLOCKS
 #define MB_SM_BLOCKS 5            // resident CTAs/SM the register budget is tuned for (measured best of 4/5/6/8)
 #endif
@@ -48,9 +57,26 @@ struct PostSmemHdr
 	float  insT[MB_MAX_K];
 	};
 
-__global__ void __launch_bounds__(32*MB_WARPS_PER_BLOCK, MB_SM_BLOCKS)
+// sum over features of the pre-multiplied pair tables, in feature order starting from 0
+// (mega.cpp:350-357); xb[f] = offset of row a_f of feature f's table, y0/y1 = packed letters of the column
+__device__ __forceinline__ float mb_mega_emit(const float *T, const uint32_t (&xb)[8], uint32_t y0, uint32_t y1, int nf)
+	{
+	float e = ADD(0.0f, T[xb[0] + (y0 & 255u)]);
+	if (nf > 1) e = ADD(e, T[xb[1] + ((y0 >> 8) & 255u)]);
+	if (nf > 2) e = ADD(e, T[xb[2] + ((y0 >> 16) & 255u)]);
+	if (nf > 3) e = ADD(e, T[xb[3] + (y0 >> 24)]);
+	if (nf > 4) e = ADD(e, T[xb[4] + (y1 & 255u)]);
+	if (nf > 5) e = ADD(e, T[xb[5] + ((y1 >> 8) & 255u)]);
+	if (nf > 6) e = ADD(e, T[xb[6] + ((y1 >> 16) & 255u)]);
+	if (nf > 7) e = ADD(e, T[xb[7] + (y1 >> 24)]);
+	return e;
+	}
+
+template <bool MEGA>
+__global__ void __launch_bounds__(32*MB_WARPS_PER_BLOCK, MEGA ? 4 : MB_SM_BLOCKS)
 k_posterior_sm(const PostParams P)
 	{
+	constexpr int NARR = MEGA ? MB_SM_ARRAYS + 1 : MB_SM_ARRAYS;
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	PostSmemHdr &sm = *reinterpret_cast<PostSmemHdr *>(smem_raw);
 	const MbHmm h = P.h;
@@ -59,19 +85,24 @@ k_posterior_sm(const PostParams P)
 	const int gwarp = blockIdx.x*MB_WARPS_PER_BLOCK + wib;
 	const int CM = (int) P.cmax;                             // columns per lane the smem is sized for
 	float *matchT = reinterpret_cast<float *>(smem_raw + sizeof(PostSmemHdr));
-	float *wbase = matchT + ((h.K*h.KS + 3) & ~3) + (size_t) wib*MB_SM_ARRAYS*CM*32;
+	const int tsize = MEGA ? (int) P.mega_tsize : h.K*h.KS;
+	float *wbase = matchT + ((tsize + 3) & ~3) + (size_t) wib*NARR*CM*32;
 	float *aS = wbase;                  // Forward: S ; EA: old row
 	float *aM = aS + CM*32;             // M        ; EA: staged posterior row (column-linear)
 	float *aIX = aM + CM*32;            //          ; EA: lane-local prefix maxima
 	float *aJX = aIX + CM*32;
 	int   *aY = reinterpret_cast<int *>(aJX + CM*32);
 	float *aE = reinterpret_cast<float *>(aY) + CM*32;
+	int   *aY2 = reinterpret_cast<int *>(aE + CM*32);       // MEGA only: letters of features 4..7
+	(void) aY2;
 
 	mb_logadd_fill(sm.coef);
-	for (int k = threadIdx.x; k < h.K; k += blockDim.x)
-		sm.insT[k] = P.insT[k];
-	for (int k = threadIdx.x; k < h.K*h.KS; k += blockDim.x)
+	if (!MEGA)
+		for (int k = threadIdx.x; k < h.K; k += blockDim.x)
+			sm.insT[k] = P.insT[k];
+	for (int k = threadIdx.x; k < tsize; k += blockDim.x)
 		matchT[k] = P.matchT[k];
+	const int nf = (int) P.mega_nf;
 	__syncthreads();
 
 	const LogAdd la = mb_logadd_make(sm.coef);
@@ -96,6 +127,12 @@ k_posterior_sm(const PostParams P)
 		const int LX = (int) P.seqlen[sx], LY = (int) P.seqlen[sy];
 		const uint8_t *Xc = P.codes + P.seqoff[sx];
 		const uint8_t *Yc = P.codes + P.seqoff[sy];
+		// MEGA: 8 letter bytes and one insert emission per position
+		const uint2 *Xl = reinterpret_cast<const uint2 *>(P.codes) + P.seqoff[sx];
+		const uint2 *Yl = reinterpret_cast<const uint2 *>(P.codes) + P.seqoff[sy];
+		const float *Xi = P.insT + P.seqoff[sx];
+		const float *Yi = P.insT + P.seqoff[sy];
+		(void) Xc; (void) Yc; (void) Xl; (void) Yl; (void) Xi; (void) Yi;
 		const int C = min(CM, (LY + 31) >> 5);            // columns per lane for this pair
 		const int W = 32*C;
 		const int nstrips = (LY + W - 1)/W;
@@ -121,9 +158,19 @@ k_posterior_sm(const PostParams P)
 			for (int c = 0; c < C; ++c)
 				{
 				const int jj = j0 + lane*C + c;
-				const int code = jj < LY ? (int) Yc[jj] : h.pad;
-				aY[c*32 + lane] = code;
-				aE[c*32 + lane] = sm.insT[code];
+				if (MEGA)
+					{
+					const uint2 yl = jj < LY ? Yl[jj] : make_uint2(0u, 0u);
+					aY[c*32 + lane] = (int) yl.x;
+					aY2[c*32 + lane] = (int) yl.y;
+					aE[c*32 + lane] = jj < LY ? Yi[jj] : 0.0f;
+					}
+				else
+					{
+					const int code = jj < LY ? (int) Yc[jj] : h.pad;
+					aY[c*32 + lane] = code;
+					aE[c*32 + lane] = sm.insT[code];
+					}
 				aS[c*32 + lane] = Z; aM[c*32 + lane] = Z; aIX[c*32 + lane] = Z; aJX[c*32 + lane] = Z;
 				}
 			float outM = Z, outAIY = Z, outAJY = Z, outS = Z;
@@ -131,18 +178,30 @@ k_posterior_sm(const PostParams P)
 			float bIX = Z, bJX = Z;
 			const int nsteps = LX + nl;
 			int xcPref = h.pad;
+			uint2 xlPref = make_uint2(0u, 0u);
+			float exPref = 0.0f;
 			for (int t = 0; t < nsteps; ++t)
 				{
 				const int i = t - lane;
 				const int xc = xcPref;
-				xcPref = (i >= 0 && i < LX) ? (int) Xc[i] : h.pad;
+				const uint2 xl = xlPref;
+				const float exm = exPref;
+				if (MEGA)
+					{
+					const bool in = i >= 0 && i < LX;
+					xlPref = in ? Xl[i] : make_uint2(0u, 0u);
+					exPref = in ? Xi[i] : 0.0f;
+					}
+				else
+					xcPref = (i >= 0 && i < LX) ? (int) Xc[i] : h.pad;
+				(void) xc; (void) xl; (void) exm;
 				float Lm = __shfl_up_sync(MB_FULL, outM, 1);
 				float Laiy = __shfl_up_sync(MB_FULL, outAIY, 1);
 				float Lajy = __shfl_up_sync(MB_FULL, outAJY, 1);
 				float Ls = __shfl_up_sync(MB_FULL, outS, 1);
 				if (i >= 0 && i <= LX && lane < nl)
 					{
-					const float ex = sm.insT[xc];
+					const float ex = MEGA ? exm : sm.insT[xc];
 					if (lane == 0)
 						{
 						if (strip == 0)
@@ -175,7 +234,14 @@ k_posterior_sm(const PostParams P)
 					float diag = dprev;
 					dprev = Ls;
 					float lm = Lm, laiy = Laiy, lajy = Lajy, sLast = Z;
-					const float *mrow = matchT + xc*h.KS;
+					const float *mrow = matchT + (MEGA ? 0 : xc*h.KS);
+					uint32_t xb[8];
+					if (MEGA)
+						{
+#pragma unroll
+						for (int f = 0; f < 8; ++f)
+							xb[f] = P.mega_base[f] + ((f < 4 ? (xl.x >> (8*f)) : (xl.y >> (8*(f - 4)))) & 255u)*P.mega_alpha[f];
+						}
 					const bool cap = last && i == LX && lane == lcl;
 					float *dst = fms + (size_t) t*W + lane;
 					const bool dump = P.dbg_fwd != nullptr && i >= 1;
@@ -185,7 +251,8 @@ MB_UNROLL(MB_SM_UNROLL)
 						const int o = c*32 + lane;
 						const float Mo = aM[o], IXo = aIX[o], JXo = aJX[o];
 						const float eyc = aE[o];
-						const float m = ADD(diag, mrow[aY[o]]);
+						const float em = MEGA ? mb_mega_emit(matchT, xb, (uint32_t) aY[o], (uint32_t) aY2[o], nf) : mrow[aY[o]];
+						const float m = ADD(diag, em);
 						const float ix = ADD(la(ADD(IXo, h.tII), ADD(Mo, h.tMI)), ex);
 						const float jx = ADD(la(ADD(JXo, h.tJJ), ADD(Mo, h.tMJ)), ex);
 						const float iy = ADD(la(laiy, ADD(lm, h.tMI)), eyc);
@@ -249,20 +316,42 @@ MB_UNROLL(MB_SM_UNROLL)
 			for (int c = 0; c < C; ++c)
 				{
 				const int jj = j0 + lane*C + c + 1;
-				const int code = jj < LY ? (int) Yc[jj] : h.pad;
-				aY[c*32 + lane] = code;
-				aE[c*32 + lane] = sm.insT[code];
+				if (MEGA)
+					{
+					const uint2 yl = jj < LY ? Yl[jj] : make_uint2(0u, 0u);
+					aY[c*32 + lane] = (int) yl.x;
+					aY2[c*32 + lane] = (int) yl.y;
+					aE[c*32 + lane] = jj < LY ? Yi[jj] : 0.0f;
+					}
+				else
+					{
+					const int code = jj < LY ? (int) Yc[jj] : h.pad;
+					aY[c*32 + lane] = code;
+					aE[c*32 + lane] = sm.insT[code];
+					}
 				aM[c*32 + lane] = Z; aIX[c*32 + lane] = Z; aJX[c*32 + lane] = Z;
 				}
 			float outM = Z, outIY = Z, outJY = Z;
 			float dprev = Z;
 			const int nsteps = LX + nl - 1;
 			int xcPref = h.pad;
+			uint2 xlPref = make_uint2(0u, 0u);
+			float exPref = 0.0f;
 			for (int u = 0; u < nsteps; ++u)
 				{
 				const int i = LX - u + (nl - 1 - lane);
 				const int xc = xcPref;
-				xcPref = (i >= 2 && i <= LX) ? (int) Xc[i - 1] : h.pad;
+				const uint2 xl = xlPref;
+				const float exm = exPref;
+				if (MEGA)
+					{
+					const bool in = i >= 2 && i <= LX;
+					xlPref = in ? Xl[i - 1] : make_uint2(0u, 0u);
+					exPref = in ? Xi[i - 1] : 0.0f;
+					}
+				else
+					xcPref = (i >= 2 && i <= LX) ? (int) Xc[i - 1] : h.pad;
+				(void) xc; (void) xl; (void) exm;
 				float Rm = __shfl_down_sync(MB_FULL, outM, 1);
 				float Riy = __shfl_down_sync(MB_FULL, outIY, 1);
 				float Rjy = __shfl_down_sync(MB_FULL, outJY, 1);
@@ -280,8 +369,15 @@ MB_UNROLL(MB_SM_UNROLL)
 							Rm = e.x; Riy = e.y; Rjy = e.z;
 							}
 						}
-					const float ex = sm.insT[xc];
-					const float *mrow = matchT + xc*h.KS;
+					const float ex = MEGA ? exm : sm.insT[xc];
+					const float *mrow = matchT + (MEGA ? 0 : xc*h.KS);
+					uint32_t xb[8];
+					if (MEGA)
+						{
+#pragma unroll
+						for (int f = 0; f < 8; ++f)
+							xb[f] = P.mega_base[f] + ((f < 4 ? (xl.x >> (8*f)) : (xl.y >> (8*(f - 4)))) & 255u)*P.mega_alpha[f];
+						}
 					uint32_t cnt = rowcnt[i - 1];
 					const uint32_t cnt0 = cnt;
 					mb200_entry *row = rows + (size_t)(i - 1)*MB_CAP;
@@ -302,7 +398,8 @@ MB_UNROLL(MB_SM_UNROLL)
 							fmNext = src[(c - 1)*32];
 						const float Mo = aM[o], IXo = aIX[o], JXo = aJX[o];
 						const float eyc = aE[o];
-						const float nM = ADD(mdiag, mrow[aY[o]]);
+						const float em = MEGA ? mb_mega_emit(matchT, xb, (uint32_t) aY[o], (uint32_t) aY2[o], nf) : mrow[aY[o]];
+						const float nM = ADD(mdiag, em);
 						const float nIX = ADD(IXo, ex);
 						const float nJX = ADD(JXo, ex);
 						const float nIY = ADD(riy, eyc);

@@ -22,7 +22,8 @@ EXPORTS = [
 	"mb200_store_exchange_begin", "mb200_store_exchange_commit", "mb200_store_entries_ptr", "mb200_store_values_changed",
 	"mb200_group_create", "mb200_group_destroy", "mb200_group_last_error", "mb200_group_size", "mb200_group_ctx",
 	"mb200_group_set_hmm", "mb200_group_set_seqs", "mb200_group_posteriors_allpairs", "mb200_group_consistency_iter",
-	"mb200_group_get_stats", "mb200_msa_reset", "mb200_msa_join", "mb200_msa_export", "mb200_guide_tree",
+	"mb200_group_get_stats", "mb200_msa_reset", "mb200_msa_join", "mb200_msa_export", "mb200_guide_tree", "mb200_set_seqs_mega",
+	"mb200_group_set_seqs_mega",
 ]
 
 
@@ -126,6 +127,22 @@ class Engine:
 		buf = np.frombuffer(b"".join(bs), dtype=np.uint8)
 		self.nseq = len(bs)
 		self._ck(self.lib.mb200_set_seqs(self.h, C.c_uint32(len(bs)), _ptr(buf), _ptr(off)))
+
+	def set_seqs_mega(self, model, profiles):
+		"""Mega feature profiles: model = dict(alpha[F], weights[F], logprobs, logprobmx), profiles = list of
+		uint8 arrays [L][F] (Mega::m_Profiles)"""
+		F = len(model["alpha"])
+		alpha = np.ascontiguousarray(model["alpha"], np.uint32)
+		w = np.ascontiguousarray(model["weights"], np.float32)
+		lp = np.ascontiguousarray(model["logprobs"], np.float32)
+		lpm = np.ascontiguousarray(model["logprobmx"], np.float32)
+		self.lens = np.array([len(p) for p in profiles], np.int64)
+		off = np.zeros(len(profiles) + 1, np.uint64)
+		off[1:] = np.cumsum(self.lens)
+		let = np.ascontiguousarray(np.concatenate([np.asarray(p, np.uint8).reshape(-1, F) for p in profiles]), np.uint8)
+		self.nseq = len(profiles)
+		self._ck(self.lib.mb200_set_seqs_mega(self.h, C.c_uint32(self.nseq), _ptr(let), _ptr(off), C.c_uint32(F), _ptr(alpha),
+		  _ptr(w), _ptr(lp), _ptr(lpm)))
 
 	# ---- posterior stage
 	def posteriors(self, pair_x, pair_y, want_ea=True, force_c=0):

@@ -17,6 +17,7 @@
 #include "muscle.h"
 #include "mpcflat.h"
 #include "pairhmm.h"
+#include "mega.h"
 #include <omp.h>
 #include <chrono>
 
@@ -390,6 +391,66 @@ int ref_upgma(uint n, const float *ea, int linkage, uint *Left, uint *Right, flo
 		RLen[k] = (float) T.GetEdgeLength(Node, Right[k]);
 		}
 	return 0;
+	}
+
+// ---------------------------------------------------------------- Mega (Muscle-3D feature profiles)
+// Mega::FromFile (mega.cpp:113), the model it derives, and CalcPost's mega branch (calcpost.cpp:14-22:
+// Mega::CalcFwdFlat_mega + CalcBwdFlat_mega, then CalcPostFlat).  One file per process (the reference
+// keeps the model in statics and asserts they are empty).
+int ref_mega_load(const char *Path)
+	{
+	Mega::FromFile(string(Path));
+	return (int) Mega::GetProfileCount();
+	}
+
+uint ref_mega_nfeat() { return Mega::GetFeatureCount(); }
+
+void ref_mega_model(uint *Alpha, float *Weights, float *LogProbs, float *LogProbMx)
+	{
+	const uint F = Mega::GetFeatureCount();
+	uint a = 0, b = 0;
+	for (uint f = 0; f < F; ++f)
+		{
+		const uint A = Mega::GetAlphaSize(f);
+		Alpha[f] = A;
+		Weights[f] = Mega::GetWeight(f);
+		for (uint x = 0; x < A; ++x)
+			{
+			LogProbs[a++] = Mega::m_LogProbsVec[f][x];
+			for (uint y = 0; y < A; ++y)
+				LogProbMx[b++] = Mega::m_LogProbMxVec[f][x][y];
+			}
+		}
+	}
+
+uint ref_mega_profile_len(uint Idx) { return SIZE(Mega::GetProfile(Idx)); }
+
+void ref_mega_profile(uint Idx, byte *Letters, char *Seq)
+	{
+	const vector<vector<byte> > &P = Mega::GetProfile(Idx);
+	const uint F = Mega::GetFeatureCount();
+	for (uint i = 0; i < SIZE(P); ++i)
+		for (uint f = 0; f < F; ++f)
+			Letters[i*F + f] = P[i][f];
+	const string &S = Mega::m_Seqs[Idx];
+	memcpy(Seq, S.c_str(), S.size() + 1);
+	}
+
+void ref_mega_calcpost(uint IdxX, uint IdxY, float *PostOut)
+	{
+	const vector<vector<byte> > &PX = Mega::GetProfile(IdxX);
+	const vector<vector<byte> > &PY = Mega::GetProfile(IdxY);
+	const uint LX = SIZE(PX), LY = SIZE(PY);
+	float *Fwd = AllocFB(LX, LY);
+	float *Bwd = AllocFB(LX, LY);
+	Mega::CalcFwdFlat_mega(PX, PY, Fwd);
+	Mega::CalcBwdFlat_mega(PX, PY, Bwd);
+	float *Post = AllocPost(LX, LY);
+	CalcPostFlat(Fwd, Bwd, LX, LY, Post);
+	memcpy(PostOut, Post, size_t(LX)*LY*sizeof(float));
+	myfree(Fwd);
+	myfree(Bwd);
+	myfree(Post);
 	}
 
 } // extern "C"

@@ -118,3 +118,15 @@ def test_align_cli_c2_matches_reference_msa(tmp_path):
 	assert r.returncode == 0, r.stderr[-2000:]
 	got, want = read_afa(out), read_afa(ref)
 	assert got == want
+
+
+def test_align_cli_mega_matches_reference_msa(tmp_path):
+	"""`-align x.mega` (Muscle-3D feature profiles, calcpost.cpp:14-22): the reference's own
+	test_data/mega/BB11001.mega through the engine's Mega emission mode"""
+	if not os.path.exists(CLI):
+		pytest.skip("integration/_build/muscle_b200 not built (needs /root/reference at build time)")
+	out = tmp_path / "bb11001.afa"
+	r = subprocess.run([CLI, "-align", os.path.join(E2E, "BB11001.mega"), "-output", str(out), "-quiet"],
+	  capture_output=True, text=True, timeout=600)
+	assert r.returncode == 0, r.stderr[-2000:]
+	assert read_afa(out) == read_afa(os.path.join(E2E, "BB11001.mega.ref.afa"))
