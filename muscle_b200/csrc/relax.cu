@@ -424,11 +424,17 @@ __global__ void k_copy_entries(uint64_t lo, uint64_t hi, const mb200_entry *__re
 static int prepare_relax_order(mb200_ctx *ctx, uint32_t p_lo, uint32_t p_hi)
 	{
 	const uint32_t n = ctx->nseq;
+	static uint32_t tile = 0;
+	if (tile == 0)
+		{
+		const char *ev = getenv("MB200_RELAX_TILE");           // tuning hook
+		tile = ev ? (uint32_t) std::max(1, atoi(ev)) : RELAX_TILE;
+		}
 	if (ctx->relax_order_n == n && ctx->relax_order_lo == p_lo && ctx->relax_order_hi == p_hi && ctx->d_relax_order.p)
 		return MB200_OK;
 	std::vector<uint32_t> order;
 	order.reserve(p_hi - p_lo);
-	const uint32_t T = RELAX_TILE;
+	const uint32_t T = tile;
 	for (uint32_t tx = 0; tx < n; tx += T)
 		for (uint32_t ty = tx; ty < n; ty += T)
 			for (uint32_t x = tx; x < std::min(n, tx + T); ++x)
