@@ -256,6 +256,11 @@ def main():
 		return
 
 	# ------------------------------------------------------------------ our arm
+	# stdout carries exactly ONE line (the JSON record): everything libraries print meanwhile (e.g. NCCL's
+	# version banner) is sent to stderr
+	sys.stdout.flush()
+	saved_stdout = os.dup(1)
+	os.dup2(2, 1)
 	import torch
 	import torch.distributed as dist
 	if not torch.cuda.is_available():
@@ -434,7 +439,10 @@ def main():
 				out["extra"] = extras(tables, args)
 			except Exception as e:           # the headline line must not die on a secondary measurement
 				out["extra"] = {"error": repr(e)}
+		sys.stdout.flush()
+		os.dup2(saved_stdout, 1)
 		print(json.dumps(out))
+		sys.stdout.flush()
 
 
 def x1_bytes_f(pipe):

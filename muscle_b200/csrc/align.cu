@@ -435,6 +435,25 @@ __global__ void k_bp_weight(const BuildPostParams P, uint32_t *__restrict__ weig
 	}
 
 #define BP_NBUF 3
+// explicit 32-bit shared-memory accesses: with plain pointers the compiler re-derives the shared window
+// base (S2UR SR_CgaCtaId + ULEA) inside the serial step loop, on the critical path of every step
+__device__ __forceinline__ float lds_f32(uint32_t a)
+	{
+	float v;
+	asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a) : "memory");
+	return v;
+	}
+__device__ __forceinline__ void sts_f32(uint32_t a, float v)
+	{
+	asm volatile("st.shared.f32 [%0], %1;" :: "r"(a), "f"(v) : "memory");
+	}
+__device__ __forceinline__ uint2 lds_u2(uint32_t a)
+	{
+	uint2 v;
+	asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a) : "memory");
+	return v;
+	}
+
 struct BpSched
 	{
 	const uint32_t *order;    // rows, heaviest first
@@ -456,6 +475,8 @@ k_bp_apply(const BuildPostParams P, const BpStage G, const BpSched S)
 	uint2 *stage = reinterpret_cast<uint2 *>(bp_smem + acc_bytes) + (size_t) wib*BP_NBUF*BP_G*BP_W;
 	const uint32_t ngroups = (P.nb + BP_G - 1)/BP_G;
 	const uint32_t rb0 = G.rb[G.s_lo];
+	const uint32_t accA = (uint32_t) __cvta_generic_to_shared(acc);
+	const uint32_t stageA = (uint32_t) __cvta_generic_to_shared(stage);
 	for (;;)
 		{
 		uint32_t k = 0;
@@ -506,9 +527,9 @@ k_bp_apply(const BuildPostParams P, const BpStage G, const BpSched S)
 					issue(g + 2);
 					__pipeline_wait_prior(2);                          // group g has landed
 					__syncwarp();
-					const uint2 *cur = stage + (size_t)(g % BP_NBUF)*BP_G*BP_W;
+					const uint32_t curA = stageA + (g % BP_NBUF)*(BP_G*BP_W*8);
 					// which steps of the group have entries at all (first entry of every slot)
-					uint32_t rest = __ballot_sync(MB_FULL, lane < nt && cur[lane*BP_W].x != BP_END);
+					uint32_t rest = __ballot_sync(MB_FULL, lane < nt && lds_u2(curA + lane*(BP_W*8)).x != BP_END);
 					// 1-deep software pipeline over the steps of the group: the next step's entry is fetched
 					// from the stage before the current one is added
 					uint2 v = make_uint2(BP_END, 0u);
@@ -517,7 +538,7 @@ k_bp_apply(const BuildPostParams P, const BpStage G, const BpSched S)
 						{
 						l = (uint32_t) __ffs(rest) - 1;
 						if (lane < BP_W)
-							v = cur[l*BP_W + lane];
+							v = lds_u2(curA + (l*BP_W + lane)*8);
 						}
 					while (rest)
 						{
@@ -528,13 +549,16 @@ k_bp_apply(const BuildPostParams P, const BpStage G, const BpSched S)
 							{
 							l2 = (uint32_t) __ffs(rest) - 1;
 							if (lane < BP_W)
-								v2 = cur[l2*BP_W + lane];
+								v2 = lds_u2(curA + (l2*BP_W + lane)*8);
 							}
 						const bool isLong = __shfl_sync(MB_FULL, v.x, 0) == BP_LONG;
 						if (!isLong)
 							{
 							if (v.x != BP_END)
-								acc[v.x] = __fadd_rn(acc[v.x], __uint_as_float(v.y));        // += w1*w2*P, unit weights
+								{
+								const uint32_t a = accA + v.x*4;
+								sts_f32(a, __fadd_rn(lds_f32(a), __uint_as_float(v.y)));        // += w1*w2*P, unit weights
+								}
 							}
 						else if (lane == 0)
 							{
@@ -545,8 +569,8 @@ k_bp_apply(const BuildPostParams P, const BpStage G, const BpSched S)
 							const uint32_t *p2c = P.p2c_b + P.p2c_b_off[t0 + l];
 							for (uint32_t e = ro[pos]; e < ro[pos + 1]; ++e)
 								{
-								const uint32_t c2 = p2c[en[e].col];
-								acc[c2] = __fadd_rn(acc[c2], en[e].p);
+								const uint32_t a = accA + p2c[en[e].col]*4;
+								sts_f32(a, __fadd_rn(lds_f32(a), en[e].p));
 								}
 							}
 						__syncwarp();

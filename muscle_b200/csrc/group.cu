@@ -96,20 +96,27 @@ int mb200_group_create(int ndev, const int *devices, mb200_group **out)
 		devs.assign(devices, devices + ndev);
 	mb200_group *g = new mb200_group();
 	g->err[0] = 0;
-	for (int d : devs)
+	// one thread per device: CUDA context creation is ~0.5 s per GPU and would otherwise be serial
+	g->ctx.assign(devs.size(), nullptr);
+	std::vector<int> rcs(devs.size(), MB200_OK);
 		{
-		mb200_ctx *c = nullptr;
-		const int rc = mb200_create(d, &c);
-		if (rc != MB200_OK)
+		std::vector<std::thread> th;
+		for (size_t k = 0; k < devs.size(); ++k)
+			th.emplace_back([&, k] { rcs[k] = mb200_create(devs[k], &g->ctx[k]); });
+		for (auto &t : th)
+			t.join();
+		}
+	for (size_t k = 0; k < devs.size(); ++k)
+		if (rcs[k] != MB200_OK)
 			{
-			gfail(nullptr, rc, "device %d: %s", d, mb200_last_error(nullptr));
+			const int rc = rcs[k];
+			gfail(nullptr, rc, "device %d: %s", devs[k], mb200_last_error(nullptr));
 			for (mb200_ctx *o : g->ctx)
-				mb200_destroy(o);
+				if (o)
+					mb200_destroy(o);
 			delete g;
 			return rc;
 			}
-		g->ctx.push_back(c);
-		}
 	g->ndev = (int) g->ctx.size();
 	// peer access between every pair of devices (NVLink / NVSwitch); without it the copies below
 	// would be staged through the host
