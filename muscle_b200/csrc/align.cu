@@ -71,14 +71,16 @@ static void trace_init()
 
 // =============================================================================================
 // decoding DP
-#define AW_C 8                       // columns per lane
+#define AW_C 4                       // columns per lane (a single warp is bound by instruction latency: narrow
+                                     // lanes put more warps on a row; measured 8 -> 4: see profiles/r02_SUMMARY.md)
 #define AW_W (32*AW_C)               // strip width
 struct AlnProblem
 	{
 	uint32_t LX, LY, ld;             // ld: row pitch of dense (multiple of AW_C, padding zero)
 	const float *dense;              // LX rows x ld
-	uint16_t *tb;                    // traceback words [LX][nstrips*32] (global), unused when the launch keeps it in smem
-	float *edge;                     // 2*(LX+1) floats, strip hand-over (only read/written when LY > AW_W)
+	uint8_t *tb;                     // traceback bytes [LX][nstrips*32] (global), unused when the launch keeps it in smem
+	uint2 *edge;                     // [npass-1][LX+1] {value, row tag}: hand-over between the CTAs of one problem (zeroed by the host)
+	uint32_t *done;                  // CTAs of the problem that have finished (zeroed by the host)
 	char *path;                      // LX+LY+1
 	float *score;
 	uint32_t *plen;                  // may be nullptr
@@ -87,12 +89,13 @@ struct AlnProblem
 #define AW_MAXW 16                   // warps per CTA = strips in flight
 #define AW_RING 64                   // rows of slack between neighbouring strips
 
-// One CTA per problem, one warp per 512-column strip (AW_MAXW strips in flight, wider problems in
-// several passes).  Inside a warp the rows are an anti-diagonal wavefront over the lanes; between
-// warps the same wavefront continues: strip w+1 consumes, row by row, the last column of strip w
-// through a shared-memory ring guarded by a progress counter, so a 5000 x 5000 join takes ~LX+32*strips
-// steps instead of LX*strips.
-// 64-bit shared-memory accesses that are guaranteed to be ONE transaction (value + row tag)
+// One warp per strip of 32*AW_C columns, AW_MAXW strips per CTA, and as many CTAs per problem
+// (blockIdx.y) as the width needs.  Inside a warp the rows are an anti-diagonal wavefront over the
+// lanes; between warps the same wavefront continues: strip w+1 consumes, row by row, the last column of
+// strip w through a shared-memory ring whose entries carry {value, row} in ONE 64-bit word (no fence),
+// and between CTAs through a global array of the same entries (the CTAs of a problem are dispatched in
+// blockIdx.y order, so a consumer never waits for a producer that cannot start).  A 4349 x 4636 join
+// therefore takes ~LX + 32*strips steps instead of LX*strips.
 __device__ __forceinline__ void ring_put(uint2 *slot, float v, int row)
 	{
 	asm volatile("st.volatile.shared.v2.u32 [%0], {%1, %2};" :: "r"((uint32_t) __cvta_generic_to_shared(slot)),
@@ -105,166 +108,184 @@ __device__ __forceinline__ uint2 ring_get(const uint2 *slot)
 	  : "r"((uint32_t) __cvta_generic_to_shared(slot)) : "memory");
 	return e;
 	}
+__device__ __forceinline__ void chan_put(uint2 *slot, float v, int row)
+	{
+	asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" :: "l"(slot), "r"(__float_as_uint(v)), "r"((uint32_t) row) : "memory");
+	}
+__device__ __forceinline__ uint2 chan_get(const uint2 *slot)
+	{
+	uint2 e;
+	asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(e.x), "=r"(e.y) : "l"(slot) : "memory");
+	return e;
+	}
 
 template <bool TB_SMEM>
 __global__ void __launch_bounds__(32*AW_MAXW)
 k_aln_wave(const AlnProblem *probs)
 	{
-	extern __shared__ uint16_t tb_sm[];
+	extern __shared__ uint8_t tb_sm[];
 	__shared__ uint2 ring[AW_MAXW][AW_RING];          // {bits of the value, row it belongs to}: one 8-byte store
 	__shared__ int cons[AW_MAXW];
-	__shared__ float finalS;
 	const AlnProblem pr = probs[blockIdx.x];
 	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 	const int NW = blockDim.x >> 5;
 	const int LX = (int) pr.LX, LY = (int) pr.LY;
 	const int nstrips = (LY + AW_W - 1)/AW_W;
-	const int npass = (nstrips + NW - 1)/NW;
-	uint16_t *tb = TB_SMEM ? tb_sm : pr.tb;
+	const int pass = blockIdx.y;                             // which group of AW_MAXW strips this CTA owns
+	if (pass*NW >= nstrips)
+		return;                                              // narrower problem of a batch
+	uint8_t *tb = TB_SMEM ? tb_sm : pr.tb;
 	volatile int *vcons = cons;
-	for (int pass = 0; pass < npass; ++pass)
+	if (lane == 0)
+		cons[wid] = 0;
+	for (int k = lane; k < AW_RING; k += 32)
+		ring[wid][k] = make_uint2(0u, 0u);                   // row tags start at 1
+	__syncthreads();
+	const int strip = pass*NW + wid;
+	bool lastStripHere = false;
+	if (strip < nstrips)
 		{
-		if (lane == 0)
-			cons[wid] = 0;
-		for (int k = lane; k < AW_RING; k += 32)
-			ring[wid][k] = make_uint2(0u, 0u);                 // row tags start at 1
-		__syncthreads();
-		const int strip = pass*NW + wid;
-		if (strip < nstrips)
+		const int j0 = strip*AW_W;
+		const int ncol = min(AW_W, LY - j0);
+		const int nl = (ncol + AW_C - 1)/AW_C;
+		const bool hasIn = strip > 0, hasOut = strip + 1 < nstrips;
+		const bool ringIn = hasIn && wid > 0;                    // else the CTA on the left hands over through global memory
+		const bool ringOut = hasOut && wid + 1 < NW;
+		const uint2 *chanIn = pr.edge + (size_t)(pass > 0 ? pass - 1 : 0)*(LX + 1);
+		uint2 *chanOut = pr.edge + (size_t) pass*(LX + 1);
+		lastStripHere = strip == nstrips - 1;
+		float old[AW_C];
+#pragma unroll
+		for (int c = 0; c < AW_C; ++c)
+			old[c] = 0.0f;                                   // row 0 (calcalnflat.cpp:15-19)
+		float outNew = 0.0f, prevRecv = 0.0f;
+		const float *src = pr.dense + j0 + lane*AW_C;
+		// rows are fetched three steps ahead: before step t the queue holds rows i, i+1, i+2 of this lane
+		float4 q0, q1, q2;
+		q0 = q1 = q2 = make_float4(0.f, 0.f, 0.f, 0.f);
+		if (lane < nl)
 			{
-			const int j0 = strip*AW_W;
-			const int ncol = min(AW_W, LY - j0);
-			const int nl = (ncol + AW_C - 1)/AW_C;
-			const bool hasIn = strip > 0, hasOut = strip + 1 < nstrips;
-			const bool ringIn = hasIn && wid > 0;                    // else the previous pass left it in global memory
-			const bool ringOut = hasOut && wid + 1 < NW;
-			const float *edgeIn = pr.edge + (size_t)(pass & 1)*(LX + 1);
-			float *edgeOut = pr.edge + (size_t)((pass + 1) & 1)*(LX + 1);
-			float old[AW_C];
-#pragma unroll
-			for (int c = 0; c < AW_C; ++c)
-				old[c] = 0.0f;                                   // row 0 (calcalnflat.cpp:15-19)
-			float outNew = 0.0f, prevRecv = 0.0f;
-			const float *src = pr.dense + j0 + lane*AW_C;
-			// rows are fetched three steps ahead (a dependent L2 round trip is ~3 steps of arithmetic):
-			// before step t the queue holds rows i, i+1, i+2 of this lane (i = t - lane + 1)
-			float4 q0a, q0b, q1a, q1b, q2a, q2b;
-			q0a = q0b = q1a = q1b = q2a = q2b = make_float4(0.f, 0.f, 0.f, 0.f);
-			if (lane < nl)
-				{
-				const int r0 = 1 - lane;                         // row of step 0
-				if (r0 >= 1 && r0 <= LX)
-					{
-					const float4 *q = reinterpret_cast<const float4 *>(src + (size_t)(r0 - 1)*pr.ld);
-					q0a = q[0]; q0b = q[1];
-					}
-				if (r0 + 1 >= 1 && r0 + 1 <= LX)
-					{
-					const float4 *q = reinterpret_cast<const float4 *>(src + (size_t)(r0)*pr.ld);
-					q1a = q[0]; q1b = q[1];
-					}
-				if (r0 + 2 >= 1 && r0 + 2 <= LX)
-					{
-					const float4 *q = reinterpret_cast<const float4 *>(src + (size_t)(r0 + 1)*pr.ld);
-					q2a = q[0]; q2b = q[1];
-					}
-				}
-			const int nsteps = LX + nl - 1;
-			// the lane that owns DP column LY (for the final score)
-			const int lastLane = (LY - 1 - j0)/AW_C, lastC = (LY - 1 - j0) % AW_C;
-			// one wavefront step; (qa,qb) holds this lane's row of the step and is refilled with the row
-			// three steps ahead.  The loop is unrolled by 3 over the three register sets: rotating them
-			// with moves would make every step wait for the load issued one step earlier.
-			auto step = [&](const int t, float4 &qa, float4 &qb)
-				{
-				const int i = t - lane + 1;                      // 1-based row
-				float recv = __shfl_up_sync(MB_FULL, outNew, 1);
-				if (lane == 0)
-					{
-					recv = 0.0f;
-					if (hasIn && i >= 1 && i <= LX)
-						{
-						if (ringIn)
-							{
-							// value and row tag travel in one 64-bit shared-memory word, so no fence is needed
-							// (a __threadfence_block here waited for this lane's outstanding GLOBAL traceback
-							// store every step: 1 us per step in the first version)
-							uint2 e;
-							do
-								e = ring_get(&ring[wid - 1][i % AW_RING]);
-							while ((int) e.y != i);                   // strip on the left has not produced row i yet
-							recv = __uint_as_float(e.x);
-							vcons[wid] = i;
-							}
-						else
-							recv = edgeIn[i];
-						}
-					}
-				const bool valid = i >= 1 && i <= LX && lane < nl;
-				float p[AW_C];
-				p[0] = qa.x; p[1] = qa.y; p[2] = qa.z; p[3] = qa.w; p[4] = qb.x; p[5] = qb.y; p[6] = qb.z; p[7] = qb.w;
-				if (lane < nl && i + 3 >= 1 && i + 3 <= LX)
-					{
-					const float4 *q = reinterpret_cast<const float4 *>(src + (size_t)(i + 2)*pr.ld);
-					qa = q[0]; qb = q[1];
-					}
-				if (valid)
-					{
-					float Y = recv;                                // new[i][first col - 1]
-					float diag = prevRecv;                         // new[i-1][first col - 1]
-					uint32_t word = 0;
-#pragma unroll
-					for (int c = 0; c < AW_C; ++c)
-						{
-						const float B = __fadd_rn(diag, p[c]);       // calcalnflat.cpp:31-37
-						const float X = old[c];
-						const float nw = fmaxf(fmaxf(B, X), Y);
-						const uint32_t code = (B >= X) ? ((B >= Y) ? 0u : 2u) : ((X >= Y) ? 1u : 2u);    // best3.h:5-28
-						word |= code << (2*c);
-						diag = X;
-						old[c] = nw;
-						Y = nw;
-						if (c == lastC && lane == lastLane && i == LX && strip == nstrips - 1)
-							finalS = nw;
-						}
-					outNew = Y;
-					tb[((size_t)(i - 1)*nstrips + strip)*32 + lane] = (uint16_t) word;
-					if (hasOut && lane == 31)
-						{
-						if (ringOut)
-							{
-							while (i > AW_RING && vcons[wid + 1] < i - AW_RING)
-								;                                     // the slot still holds an unconsumed row
-							ring_put(&ring[wid][i % AW_RING], outNew, i);
-							}
-						else
-							edgeOut[i] = outNew;
-						}
-					}
-				prevRecv = recv;
-				__syncwarp();
-				};
-			int t = 0;
-			for (; t + 2 < nsteps; t += 3)
-				{
-				step(t, q0a, q0b);
-				step(t + 1, q1a, q1b);
-				step(t + 2, q2a, q2b);
-				}
-			if (t < nsteps)
-				step(t, q0a, q0b);
-			if (t + 1 < nsteps)
-				step(t + 1, q1a, q1b);
+			const int r0 = 1 - lane;                         // row of step 0
+			if (r0 >= 1 && r0 <= LX)
+				q0 = *reinterpret_cast<const float4 *>(src + (size_t)(r0 - 1)*pr.ld);
+			if (r0 + 1 >= 1 && r0 + 1 <= LX)
+				q1 = *reinterpret_cast<const float4 *>(src + (size_t)(r0)*pr.ld);
+			if (r0 + 2 >= 1 && r0 + 2 <= LX)
+				q2 = *reinterpret_cast<const float4 *>(src + (size_t)(r0 + 1)*pr.ld);
 			}
-		__syncthreads();
+		const int nsteps = LX + nl - 1;
+		// the lane that owns DP column LY (for the final score)
+		const int lastLane = (LY - 1 - j0)/AW_C, lastC = (LY - 1 - j0) % AW_C;
+		// one wavefront step; q holds this lane's row of the step and is refilled with the row three
+		// steps ahead.  The loop is unrolled by 3 over the three register sets (rotating them with moves
+		// would make every step wait for the load issued one step earlier).
+		auto step = [&](const int t, float4 &q)
+			{
+			const int i = t - lane + 1;                      // 1-based row
+			float recv = __shfl_up_sync(MB_FULL, outNew, 1);
+			if (lane == 0)
+				{
+				recv = 0.0f;
+				if (hasIn && i >= 1 && i <= LX)
+					{
+					uint2 e;
+					if (ringIn)
+						{
+						do
+							e = ring_get(&ring[wid - 1][i % AW_RING]);
+						while ((int) e.y != i);                   // strip on the left has not produced row i yet
+						vcons[wid] = i;
+						}
+					else
+						{
+						do
+							e = chan_get(chanIn + i);
+						while ((int) e.y != i);
+						}
+					recv = __uint_as_float(e.x);
+					}
+				}
+			const bool valid = i >= 1 && i <= LX && lane < nl;
+			const float p[AW_C] = { q.x, q.y, q.z, q.w };
+			if (lane < nl && i + 3 >= 1 && i + 3 <= LX)
+				q = *reinterpret_cast<const float4 *>(src + (size_t)(i + 2)*pr.ld);
+			if (valid)
+				{
+				float Y = recv;                                // new[i][first col - 1]
+				float diag = prevRecv;                         // new[i-1][first col - 1]
+				uint32_t word = 0;
+#pragma unroll
+				for (int c = 0; c < AW_C; ++c)
+					{
+					const float B = __fadd_rn(diag, p[c]);       // calcalnflat.cpp:31-37
+					const float X = old[c];
+					const float nw = fmaxf(fmaxf(B, X), Y);
+					const uint32_t code = (B >= X) ? ((B >= Y) ? 0u : 2u) : ((X >= Y) ? 1u : 2u);    // best3.h:5-28
+					word |= code << (2*c);
+					diag = X;
+					old[c] = nw;
+					Y = nw;
+					if (c == lastC && lane == lastLane && i == LX && lastStripHere)
+						*pr.score = nw;
+					}
+				outNew = Y;
+				tb[((size_t)(i - 1)*nstrips + strip)*32 + lane] = (uint8_t) word;
+				if (hasOut && lane == 31)
+					{
+					if (ringOut)
+						{
+						while (i > AW_RING && vcons[wid + 1] < i - AW_RING)
+							;                                     // the slot still holds an unconsumed row
+						ring_put(&ring[wid][i % AW_RING], outNew, i);
+						}
+					else
+						chan_put(chanOut + i, outNew, i);
+					}
+				}
+			prevRecv = recv;
+			__syncwarp();
+			};
+		int t = 0;
+		for (; t + 2 < nsteps; t += 3)
+			{
+			step(t, q0);
+			step(t + 1, q1);
+			step(t + 2, q2);
+			}
+		if (t < nsteps)
+			step(t, q0);
+		if (t + 1 < nsteps)
+			step(t + 1, q1);
 		}
-	// traceback (tracebackflat.cpp:3-37): TB(0,j) = 'Y', TB(i,0) = 'X'.  Warp 0, all lanes in lockstep
-	// on the same (i,j); the lanes hold the traceback words of 32 consecutive rows of the current
-	// 8-column group so that a dependent load is needed only every few steps.
+	__syncthreads();
+	// traceback (tracebackflat.cpp:3-37): TB(0,j) = 'Y', TB(i,0) = 'X'.  Done by warp 0 of the CTA that
+	// finishes last (the one owning the last strip), all lanes in lockstep on the same (i,j); the lanes
+	// hold the traceback bytes of 32 consecutive rows of the current 4-column group so that a dependent
+	// load is needed only every few steps.
+	const int npass = (nstrips + NW - 1)/NW;
+	if ((pass + 1)*NW < nstrips)
+		{
+		// not the last CTA of the problem: publish the traceback bytes and leave
+		if (threadIdx.x == 0)
+			{
+			__threadfence();
+			atomicAdd(pr.done, 1u);
+			}
+		return;
+		}
 	if (wid != 0)
 		return;
+	if (npass > 1)
+		{
+		if (lane == 0)
+			while (atomicAdd(pr.done, 0u) < (uint32_t)(npass - 1))
+				;
+		__syncwarp();
+		__threadfence();
+		}
 	uint32_t n = 0;
 		{
+		const uint8_t *tbb = tb;
 		int i = LX, j = LY;
 		int cbase = -1, cidx = -1;
 		uint32_t cw = 0;
@@ -284,7 +305,7 @@ k_aln_wave(const AlnProblem *probs)
 					{
 					cbase = i; cidx = idx; d = 0;
 					const int r = i - lane;
-					cw = r >= 1 ? (uint32_t) tb[(size_t)(r - 1)*nstrips*32 + idx] : 0u;
+					cw = r >= 1 ? (uint32_t) __ldcv(tbb + (size_t)(r - 1)*nstrips*32 + idx) : 0u;
 					}
 				const uint32_t w = __shfl_sync(MB_FULL, cw, d);
 				const uint32_t code = (w >> (2*(jj % AW_C))) & 3u;
@@ -300,7 +321,6 @@ k_aln_wave(const AlnProblem *probs)
 		if (lane == 0)
 			{
 			pr.path[n] = 0;
-			*pr.score = finalS;
 			if (pr.plen)
 				*pr.plen = n;
 			}
@@ -774,7 +794,7 @@ static inline size_t al256(size_t b) { return (b + 255)/256*256; }
 struct JoinBufs                       // carved out of ctx->d_join
 	{
 	float *post; uint32_t ld;
-	uint16_t *tb; float *edge; char *path; float *score; uint32_t *plen; AlnProblem *prob;
+	uint8_t *tb; uint2 *edge; char *path; float *score; uint32_t *plen; AlnProblem *prob;
 	};
 
 // BuildPost + decoding DP of groups whose maps are already on the device.  Leaves path / plen /
@@ -787,12 +807,15 @@ static int join_core(mb200_ctx *ctx, uint32_t na, uint32_t nb, const uint32_t *d
 	const uint32_t ld = (cols_b + AW_C - 1)/AW_C*AW_C;
 	const uint32_t nstrips = (cols_b + AW_W - 1)/AW_W;
 	const size_t post_bytes = (size_t) cols_a*ld*sizeof(float);
-	const size_t tbw = (size_t) cols_a*nstrips*32*sizeof(uint16_t);
-	const bool tb_smem = tbw <= 192*1024;
+	const uint32_t nwarps = std::min<uint32_t>(AW_MAXW, nstrips);
+	const uint32_t npass = (nstrips + nwarps - 1)/nwarps;
+	const size_t tbw = (size_t) cols_a*nstrips*32;
+	const bool tb_smem = npass == 1 && tbw <= 192*1024;
+	const size_t chan_bytes = al256((size_t) npass*((size_t) cols_a + 1)*sizeof(uint2) + 256);
 	char *p = scratch;
 	B.post = (float *) p;            p += al256(post_bytes);
-	B.tb = (uint16_t *) p;           p += tb_smem ? 256 : al256(tbw);
-	B.edge = (float *) p;            p += al256(2*((size_t) cols_a + 1)*sizeof(float));
+	B.tb = (uint8_t *) p;            p += tb_smem ? 256 : al256(tbw);
+	B.edge = (uint2 *) p;            p += chan_bytes;
 	B.path = p;                      p += al256((size_t) cols_a + cols_b + 16);
 	B.score = (float *) p;           p += 256;
 	B.plen = (uint32_t *) p;         p += 256;
@@ -873,16 +896,18 @@ static int join_core(mb200_ctx *ctx, uint32_t na, uint32_t nb, const uint32_t *d
 	CU(cudaGetLastError());
 	AlnProblem pr;
 	pr.LX = cols_a; pr.LY = cols_b; pr.ld = ld; pr.dense = B.post; pr.tb = B.tb; pr.edge = B.edge;
+	pr.done = (uint32_t *)((char *) B.edge + chan_bytes - 256);
+	if (npass > 1)
+		CU(cudaMemsetAsync(B.edge, 0, chan_bytes, st));
 	pr.path = B.path; pr.score = B.score; pr.plen = B.plen;
 	CU(cudaMemcpyAsync(B.prob, &pr, sizeof pr, cudaMemcpyHostToDevice, st));
-	const uint32_t nwarps = std::min<uint32_t>(AW_MAXW, nstrips);
 	if (tb_smem)
 		{
 		CU(cudaFuncSetAttribute(k_aln_wave<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) std::max<size_t>(tbw, 16)));
 		k_aln_wave<true><<<1, 32*nwarps, tbw, st>>>(B.prob);
 		}
 	else
-		k_aln_wave<false><<<1, 32*nwarps, 0, st>>>(B.prob);
+		k_aln_wave<false><<<dim3(1, npass), 32*nwarps, 0, st>>>(B.prob);
 	CU(cudaGetLastError());
 	ctx->stats.kernel_launches++;
 	const double g1 = g_t[1], g2 = g_t[2], g3 = g_t[3];
@@ -897,7 +922,7 @@ static size_t join_scratch_bytes(uint32_t cols_a, uint32_t cols_b)
 	{
 	const uint32_t ld = (cols_b + AW_C - 1)/AW_C*AW_C;
 	const uint32_t nstrips = (cols_b + AW_W - 1)/AW_W;
-	return al256((size_t) cols_a*ld*4) + al256((size_t) cols_a*nstrips*32*2) + al256(2*((size_t) cols_a + 1)*4)
+	return al256((size_t) cols_a*ld*4) + al256((size_t) cols_a*nstrips*32) + al256((size_t)(nstrips/AW_MAXW + 1)*((size_t) cols_a + 1)*8 + 256)
 	  + al256((size_t) cols_a + cols_b + 16) + 4*256;
 	}
 
@@ -947,8 +972,8 @@ int mb200_align_pairs(mb200_ctx *ctx, uint32_t n, const uint32_t *store_pairs, c
 		const uint32_t ld = (LY + AW_C - 1)/AW_C*AW_C;
 		const uint32_t nstrips = (LY + AW_W - 1)/AW_W;
 		dense_total += al256((uint64_t) LX*ld*4);
-		tb_total += al256((uint64_t) LX*nstrips*32*2);
-		edge_total += al256(2*((uint64_t) LX + 1)*4);
+		tb_total += al256((uint64_t) LX*nstrips*32);
+		edge_total += al256((uint64_t)(nstrips/AW_MAXW + 1)*((uint64_t) LX + 1)*8 + 256);
 		lxmax = std::max(lxmax, LX);
 		maxstrips = std::max(maxstrips, nstrips);
 		}
@@ -973,8 +998,9 @@ int mb200_align_pairs(mb200_ctx *ctx, uint32_t n, const uint32_t *store_pairs, c
 		AlnProblem &q = probs[k];
 		q.LX = LX; q.LY = LY; q.ld = ld;
 		q.dense = (const float *)(d_dense + od);
-		q.tb = (uint16_t *)(d_tb + ot);
-		q.edge = (float *)(d_edge + oe);
+		q.tb = (uint8_t *)(d_tb + ot);
+		q.edge = (uint2 *)(d_edge + oe);
+		q.done = (uint32_t *)(d_edge + oe + al256((uint64_t)(nstrips/AW_MAXW + 1)*((uint64_t) LX + 1)*8 + 256) - 256);
 		q.path = d_paths + path_off[k];
 		q.score = d_scores + k;
 		q.plen = nullptr;
@@ -984,8 +1010,8 @@ int mb200_align_pairs(mb200_ctx *ctx, uint32_t n, const uint32_t *store_pairs, c
 		j.dense = (float *)(d_dense + od);
 		j.LX = LX; j.ld = ld;
 		od += al256((uint64_t) LX*ld*4);
-		ot += al256((uint64_t) LX*nstrips*32*2);
-		oe += al256(2*((uint64_t) LX + 1)*4);
+		ot += al256((uint64_t) LX*nstrips*32);
+		oe += al256((uint64_t)(nstrips/AW_MAXW + 1)*((uint64_t) LX + 1)*8 + 256);
 		}
 	CU(cudaMemsetAsync(d_dense, 0, dense_total, st));
 	CU(cudaMemcpyAsync(d_probs, probs.data(), n*sizeof(AlnProblem), cudaMemcpyHostToDevice, st));
@@ -993,7 +1019,11 @@ int mb200_align_pairs(mb200_ctx *ctx, uint32_t n, const uint32_t *store_pairs, c
 	const uint64_t warps = (uint64_t) n*lxmax;
 	k_densify<<<(uint32_t)((warps*32 + 255)/256), 256, 0, st>>>(d_jobs, n, lxmax);
 	CU(cudaGetLastError());
-	k_aln_wave<false><<<n, 32*std::min<uint32_t>(AW_MAXW, maxstrips), 0, st>>>(d_probs);
+	{
+	const uint32_t bw = std::min<uint32_t>(AW_MAXW, maxstrips);
+	CU(cudaMemsetAsync(d_edge, 0, edge_total, st));
+	k_aln_wave<false><<<dim3(n, (maxstrips + bw - 1)/bw), 32*bw, 0, st>>>(d_probs);
+	}
 	CU(cudaGetLastError());
 	ctx->stats.kernel_launches += 2;
 	CU(cudaMemcpyAsync(paths_out, d_paths, path_total, cudaMemcpyDeviceToHost, st));

@@ -99,18 +99,17 @@ def test_msa_join_rejects_bad_groups(engine):
 		  [0], [np.arange(len(seqs[0]), dtype=np.uint32)], len(seqs[0]))
 
 
-def test_decoder_wide_and_tall(engine, oracle):
-	"""k_aln_wave beyond one 512-column strip and with the traceback words in global memory: a pair of
-	long sequences through mb200_align_pairs against the oracle's CalcAlnFlat"""
-	rng = np.random.default_rng(5)
-	a = synth.make_family(2, 1300, 10, seed=77)
+@pytest.mark.parametrize("L", [1300, 2600])
+def test_decoder_wide_and_tall(engine, oracle, L):
+	"""k_aln_wave beyond one CTA (16 strips of 128 columns = 2048) and with the traceback bytes in global
+	memory: a pair of long sequences through mb200_align_pairs against the oracle's CalcAlnFlat"""
+	a = synth.make_family(2, L, L//8, seed=77)
 	engine.set_seqs(a)
 	engine.posteriors_allpairs()
 	offs, ents = engine.export_all()
 	scores, paths = engine.align_pairs([0])
 	dense = np.zeros((len(a[0]), len(a[1])), np.float32)
-	for i in range(len(a[0])):
-		for e in range(offs[0][i], offs[0][i + 1]):
-			dense[i, ents[0]["col"][e]] = ents[0]["p"][e]
+	rows = np.repeat(np.arange(len(a[0])), np.diff(offs[0].astype(np.int64)))
+	dense[rows, ents[0]["col"]] = ents[0]["p"]
 	s, path = oracle.calcaln(dense)
 	assert np.float32(s) == scores[0] and path == paths[0]
