@@ -305,7 +305,10 @@ k_aln_wave(const AlnProblem *probs)
 					{
 					cbase = i; cidx = idx; d = 0;
 					const int r = i - lane;
-					cw = r >= 1 ? (uint32_t) __ldcv(tbb + (size_t)(r - 1)*nstrips*32 + idx) : 0u;
+					cw = 0u;
+					if (r >= 1)
+						cw = TB_SMEM ? (uint32_t) tbb[(size_t)(r - 1)*nstrips*32 + idx]
+						             : (uint32_t) __ldcv(tbb + (size_t)(r - 1)*nstrips*32 + idx);    // other CTAs wrote it
 					}
 				const uint32_t w = __shfl_sync(MB_FULL, cw, d);
 				const uint32_t code = (w >> (2*(jj % AW_C))) & 3u;
