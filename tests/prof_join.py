@@ -1,5 +1,5 @@
 """profiling helper: refinement-size joins on the device-resident MSA of one synthetic workload
-    python tests/prof_join.py C3 [n_refine]"""
+    python tests/prof_join.py C3|S20 [n_refine]"""
 import os
 import random
 import sys
@@ -13,7 +13,7 @@ from muscle_b200.engine import Engine     # noqa: E402
 
 cfg = sys.argv[1] if len(sys.argv) > 1 else "C3"
 nref = int(sys.argv[2]) if len(sys.argv) > 2 else 3
-seqs = synth.make_config(cfg)
+seqs = synth.make_config("C5")[:int(cfg[1:])] if cfg.startswith("S") else synth.make_config(cfg)   # S20 = 20 proteins of ~300
 n = len(seqs)
 e = Engine(0)
 e.set_hmm(load_tables())
