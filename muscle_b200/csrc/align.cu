@@ -8,7 +8,8 @@
 // MultiSequence::Project (project.cpp:16-69) on position->column maps, i.e. the data path of
 // MPCFlat::ProgAln (progalnflat.cpp:41-71) and MPCFlat::RefineIter (refineflat.cpp:4-31).
 //
-// Decoding DP (k_aln_wave).  One CTA per problem, one warp per 512-column strip; lane l owns 16
+// Decoding DP (k_aln_wave).  One warp per 128-column strip (up to 16 strips per CTA, several CTAs per
+// problem when it is wider); lane l owns 4
 // consecutive columns and the rows are swept as an anti-diagonal wavefront (lane l is on row t-l at
 // step t, the left neighbour's value arrives by one shuffle, the left strip's through a shared-memory
 // ring), exactly the reference's recurrence
@@ -16,7 +17,7 @@
 // evaluated with the same fp32 add and the same operands, so scores are bit-identical; the
 // traceback letter follows Best3's tie rule (B if B>=X and B>=Y; else Y if B>=X; else X if X>=Y else
 // Y) and is stored as 2 bits per cell (shared memory when it fits, else global), then walked by
-// warp 0 (32 rows of traceback words cached across the lanes) and reversed.  Round 1 used one CTA
+// warp 0 (an 8-row x 16-column tile of traceback bytes cached across the lanes) and reversed.  Round 1 used one CTA
 // with 4+ barriers per row and a serial traceback through global memory.
 //
 // BuildPost.  Every cell is a sum over (s,t) in the reference's s-major/t-minor order with at most
@@ -77,7 +78,7 @@ static void trace_init()
 struct AlnProblem
 	{
 	uint32_t LX, LY, ld;             // ld: row pitch of dense (multiple of AW_C, padding zero)
-	const float *dense;              // LX rows x ld
+	const float *dense;              // LX rows x ld, preceded by one row of zeros and followed by AW_PAD_BOT readable rows
 	uint8_t *tb;                     // traceback bytes [LX][nstrips*32] (global), unused when the launch keeps it in smem
 	uint2 *edge;                     // [npass-1][LX+1] {value, row tag}: hand-over between the CTAs of one problem (zeroed by the host)
 	uint32_t *done;                  // CTAs of the problem that have finished (zeroed by the host)
@@ -88,6 +89,10 @@ struct AlnProblem
 
 #define AW_MAXW 16                   // warps per CTA = strips in flight
 #define AW_RING 64                   // rows of slack between neighbouring strips
+#ifndef AW_PF
+#define AW_PF 6                      // rows of the dense matrix in flight per lane
+#endif
+#define AW_PAD_BOT (AW_PF + 31)       // readable rows below row LX of a dense matrix (loads are not predicated)
 
 // One warp per strip of 32*AW_C columns, AW_MAXW strips per CTA, and as many CTAs per problem
 // (blockIdx.y) as the width needs.  Inside a warp the rows are an anti-diagonal wavefront over the
@@ -119,6 +124,175 @@ __device__ __forceinline__ uint2 chan_get(const uint2 *slot)
 	return e;
 	}
 
+__device__ __forceinline__ uint2 lds_v2_volatile(uint32_t addr)
+	{
+	uint2 e;
+	asm volatile("ld.volatile.shared.v2.u32 {%0, %1}, [%2];" : "=r"(e.x), "=r"(e.y) : "r"(addr) : "memory");
+	return e;
+	}
+__device__ __forceinline__ void sts_v2_volatile(uint32_t addr, float v, int row)
+	{
+	asm volatile("st.volatile.shared.v2.u32 [%0], {%1, %2};" :: "r"(addr), "r"(__float_as_uint(v)), "r"((uint32_t) row) : "memory");
+	}
+__device__ __forceinline__ int lds_volatile(uint32_t addr)
+	{
+	int v;
+	asm volatile("ld.volatile.shared.s32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+	return v;
+	}
+
+// The strip loop is written for a warp that is ALONE on its scheduler: what matters is the length of
+// the dependent chain and the number of issue slots of one step, not occupancy.  (ncu of the first
+// version on a 900 x 900 join, profiles/r02_SUMMARY.md: 350 issued instructions and ~1750 cycles per
+// step -- the lane-0 spin loop left the warp split in two for the whole step, every address was
+// recomputed from (i, strip, lane) in 64-bit arithmetic, and predicated row loads forced register copies.)
+// Here: every lane polls the same ring slot, so the wait loop is warp-uniform and nothing diverges; cells
+// are computed unconditionally and only the traceback store is predicated; the dense matrix has one zero
+// row above row 1 and AW_PAD_BOT readable rows below row LX, so the row loads need no predicate either
+// (rows < 1 read the zero row and keep the wavefront at 0, rows > LX compute values nobody reads); all
+// addresses advance by constants; the hand-over mode of a strip (none / shared ring / global channel on
+// either side) is a template parameter.
+struct AwLinks
+	{
+	uint32_t ringInBase, ringOutBase, consSelf, consNext;    // shared-memory addresses
+	const uint2 *chanIn; uint2 *chanOut;
+	};
+
+template <bool TB_SMEM, int IN, int OUT>                     // 0: none, 1: shared-memory ring, 2: global channel
+__device__ __forceinline__ void aw_strip(const AlnProblem &pr, const AwLinks &K, uint32_t tb_sm_base, int strip, int nstrips, int lane)
+	{
+	const int LX = (int) pr.LX, LY = (int) pr.LY;
+	const int j0 = strip*AW_W;
+	const int ncol = min(AW_W, LY - j0);
+	const int nl = (ncol + AW_C - 1)/AW_C;
+	const bool laneOn = lane < nl;
+	float old[AW_C];
+#pragma unroll
+	for (int c = 0; c < AW_C; ++c)
+		old[c] = 0.0f;                                       // row 0 (calcalnflat.cpp:15-19)
+	float outNew = 0.0f, prevRecv = 0.0f;
+	// rows are fetched AW_PF steps ahead: before step t the queue holds rows i .. i+AW_PF-1 of this lane,
+	// one register set per step of the unrolled loop.  Row index -1 is the zero row.
+	const long long ldb = (long long) pr.ld*(long long) sizeof(float);
+	const long long base = (long long)(size_t)(pr.dense + j0 + (laneOn ? lane : 0)*AW_C);
+	float4 q[AW_PF];
+	int i = 1 - lane;                                        // 1-based row of this lane at step t
+#pragma unroll
+	for (int u = 0; u < AW_PF; ++u)
+		q[u] = *reinterpret_cast<const float4 *>((size_t)(base + (long long) max(i + u - 1, -1)*ldb));
+	long long nxt = base + (long long) max(i + AW_PF - 1, -1)*ldb;      // row i+AW_PF of this lane
+	const int tbstep = nstrips*32;
+	// traceback byte of (row i, this lane's column group); advanced every step, used only for rows 1..LX
+	long long tbg = (long long)(size_t) pr.tb + ((long long)(i - 1)*nstrips + strip)*32 + lane;
+	uint32_t tbs = tb_sm_base + (uint32_t)(((i - 1)*nstrips + strip)*32 + lane);
+	const int nsteps = LX + nl - 1;
+	auto step = [&](const int t, float4 &q)
+		{
+		float recv = __shfl_up_sync(MB_FULL, outNew, 1);
+		float in = 0.0f;
+		if (IN != 0)
+			{
+			const int i0 = t + 1;                            // row of lane 0 (warp-uniform)
+			if (i0 <= LX)
+				{
+				uint2 e;
+				if (IN == 1)
+					{
+					const uint32_t slot = K.ringInBase + ((uint32_t)(i0 & (AW_RING - 1)) << 3);
+					do
+						e = lds_v2_volatile(slot);           // all lanes read the same word: the loop is uniform
+					while ((int) e.y != i0);                 // strip on the left has not produced row i0 yet
+					if (lane == 0)
+						asm volatile("st.volatile.shared.s32 [%0], %1;" :: "r"(K.consSelf), "r"(i0) : "memory");
+					}
+				else
+					{
+					do
+						e = chan_get(K.chanIn + i0);
+					while ((int) e.y != i0);
+					}
+				in = __uint_as_float(e.x);
+				}
+			}
+		if (lane == 0)
+			recv = in;
+		const float4 pv = q;
+		float Bv[AW_C];
+		Bv[0] = __fadd_rn(prevRecv, pv.x);                   // calcalnflat.cpp:31-37: old[j-1] + P[i][j]
+		Bv[1] = __fadd_rn(old[0], pv.y);
+		Bv[2] = __fadd_rn(old[1], pv.z);
+		Bv[3] = __fadd_rn(old[2], pv.w);
+		q = *reinterpret_cast<const float4 *>((size_t) nxt);
+		if (i >= -AW_PF)
+			nxt += ldb;
+		float Y = recv;                                      // new[i][first col - 1]
+		uint32_t word = 0;
+#pragma unroll
+		for (int c = 0; c < AW_C; ++c)
+			{
+			const float B = Bv[c];
+			const float X = old[c];
+			const float M = fmaxf(B, X);
+			const uint32_t mcode = (B >= X) ? 0u : 1u;       // best3.h:5-28: B if B>=X and B>=Y; X if X>B and X>=Y; else Y
+			const uint32_t code = (M >= Y) ? mcode : 2u;
+			const float nw = fmaxf(M, Y);
+			word |= code << (2*c);
+			old[c] = nw;
+			Y = nw;
+			}
+		outNew = Y;
+		if (laneOn && (unsigned)(i - 1) < (unsigned) LX)
+			{
+			if (TB_SMEM)
+				asm volatile("st.shared.u8 [%0], %1;" :: "r"(tbs), "r"(word) : "memory");
+			else
+				*reinterpret_cast<uint8_t *>((size_t) tbg) = (uint8_t) word;
+			}
+		tbs += (uint32_t) tbstep;
+		tbg += tbstep;
+		if (OUT != 0)
+			{
+			const int i31 = t - 30;                          // row of lane 31 (warp-uniform)
+			if (i31 >= 1 && i31 <= LX)
+				{
+				if (OUT == 1)
+					{
+					while (lds_volatile(K.consNext) < i31 - AW_RING)
+						;                                     // the slot still holds an unconsumed row
+					if (lane == 31)
+						sts_v2_volatile(K.ringOutBase + ((uint32_t)(i31 & (AW_RING - 1)) << 3), outNew, i31);
+					}
+				else if (lane == 31)
+					chan_put(K.chanOut + i31, outNew, i31);
+				}
+			}
+		prevRecv = recv;
+		++i;
+		};
+	int t = 0;
+	for (; t + AW_PF <= nsteps; t += AW_PF)
+		{
+#pragma unroll
+		for (int u = 0; u < AW_PF; ++u)
+			step(t + u, q[u]);
+		}
+#pragma unroll
+	for (int u = 0; u < AW_PF; ++u)
+		if (t + u < nsteps)
+			step(t + u, q[u]);
+	if (strip == nstrips - 1 && lane == nl - 1)
+		{
+		// the lane that owns DP column LY finished row LX in the last step
+		const int lastC = (LY - 1 - j0) % AW_C;
+		float v = old[0];
+#pragma unroll
+		for (int c = 1; c < AW_C; ++c)
+			if (c == lastC)
+				v = old[c];
+		*pr.score = v;
+		}
+	}
+
 template <bool TB_SMEM>
 __global__ void __launch_bounds__(32*AW_MAXW)
 k_aln_wave(const AlnProblem *probs)
@@ -134,134 +308,54 @@ k_aln_wave(const AlnProblem *probs)
 	const int pass = blockIdx.y;                             // which group of AW_MAXW strips this CTA owns
 	if (pass*NW >= nstrips)
 		return;                                              // narrower problem of a batch
-	uint8_t *tb = TB_SMEM ? tb_sm : pr.tb;
-	volatile int *vcons = cons;
 	if (lane == 0)
 		cons[wid] = 0;
 	for (int k = lane; k < AW_RING; k += 32)
 		ring[wid][k] = make_uint2(0u, 0u);                   // row tags start at 1
 	__syncthreads();
 	const int strip = pass*NW + wid;
-	bool lastStripHere = false;
 	if (strip < nstrips)
 		{
-		const int j0 = strip*AW_W;
-		const int ncol = min(AW_W, LY - j0);
-		const int nl = (ncol + AW_C - 1)/AW_C;
 		const bool hasIn = strip > 0, hasOut = strip + 1 < nstrips;
-		const bool ringIn = hasIn && wid > 0;                    // else the CTA on the left hands over through global memory
-		const bool ringOut = hasOut && wid + 1 < NW;
-		const uint2 *chanIn = pr.edge + (size_t)(pass > 0 ? pass - 1 : 0)*(LX + 1);
-		uint2 *chanOut = pr.edge + (size_t) pass*(LX + 1);
-		lastStripHere = strip == nstrips - 1;
-		float old[AW_C];
-#pragma unroll
-		for (int c = 0; c < AW_C; ++c)
-			old[c] = 0.0f;                                   // row 0 (calcalnflat.cpp:15-19)
-		float outNew = 0.0f, prevRecv = 0.0f;
-		const float *src = pr.dense + j0 + lane*AW_C;
-		// rows are fetched three steps ahead: before step t the queue holds rows i, i+1, i+2 of this lane
-		float4 q0, q1, q2;
-		q0 = q1 = q2 = make_float4(0.f, 0.f, 0.f, 0.f);
-		if (lane < nl)
+		const int inMode = !hasIn ? 0 : (wid > 0 ? 1 : 2);      // the CTA on the left hands over through global memory
+		const int outMode = !hasOut ? 0 : (wid + 1 < NW ? 1 : 2);
+		AwLinks K;
+		K.chanIn = pr.edge + (size_t)(pass > 0 ? pass - 1 : 0)*(LX + 1);
+		K.chanOut = pr.edge + (size_t) pass*(LX + 1);
+		K.ringInBase = (uint32_t) __cvta_generic_to_shared(&ring[wid > 0 ? wid - 1 : 0][0]);
+		K.ringOutBase = (uint32_t) __cvta_generic_to_shared(&ring[wid][0]);
+		K.consSelf = (uint32_t) __cvta_generic_to_shared(&cons[wid]);
+		K.consNext = (uint32_t) __cvta_generic_to_shared(&cons[wid + 1 < AW_MAXW ? wid + 1 : wid]);
+		const uint32_t tbb = (uint32_t) __cvta_generic_to_shared(tb_sm);
+		if (TB_SMEM)
 			{
-			const int r0 = 1 - lane;                         // row of step 0
-			if (r0 >= 1 && r0 <= LX)
-				q0 = *reinterpret_cast<const float4 *>(src + (size_t)(r0 - 1)*pr.ld);
-			if (r0 + 1 >= 1 && r0 + 1 <= LX)
-				q1 = *reinterpret_cast<const float4 *>(src + (size_t)(r0)*pr.ld);
-			if (r0 + 2 >= 1 && r0 + 2 <= LX)
-				q2 = *reinterpret_cast<const float4 *>(src + (size_t)(r0 + 1)*pr.ld);
+			// one CTA per problem: no global channel
+			if (inMode == 0 && outMode == 0)      aw_strip<TB_SMEM, 0, 0>(pr, K, tbb, strip, nstrips, lane);
+			else if (inMode == 0)                 aw_strip<TB_SMEM, 0, 1>(pr, K, tbb, strip, nstrips, lane);
+			else if (outMode == 0)                aw_strip<TB_SMEM, 1, 0>(pr, K, tbb, strip, nstrips, lane);
+			else                                  aw_strip<TB_SMEM, 1, 1>(pr, K, tbb, strip, nstrips, lane);
 			}
-		const int nsteps = LX + nl - 1;
-		// the lane that owns DP column LY (for the final score)
-		const int lastLane = (LY - 1 - j0)/AW_C, lastC = (LY - 1 - j0) % AW_C;
-		// one wavefront step; q holds this lane's row of the step and is refilled with the row three
-		// steps ahead.  The loop is unrolled by 3 over the three register sets (rotating them with moves
-		// would make every step wait for the load issued one step earlier).
-		auto step = [&](const int t, float4 &q)
+		else
 			{
-			const int i = t - lane + 1;                      // 1-based row
-			float recv = __shfl_up_sync(MB_FULL, outNew, 1);
-			if (lane == 0)
+			switch (inMode*3 + outMode)
 				{
-				recv = 0.0f;
-				if (hasIn && i >= 1 && i <= LX)
-					{
-					uint2 e;
-					if (ringIn)
-						{
-						do
-							e = ring_get(&ring[wid - 1][i % AW_RING]);
-						while ((int) e.y != i);                   // strip on the left has not produced row i yet
-						vcons[wid] = i;
-						}
-					else
-						{
-						do
-							e = chan_get(chanIn + i);
-						while ((int) e.y != i);
-						}
-					recv = __uint_as_float(e.x);
-					}
+				case 0: aw_strip<false, 0, 0>(pr, K, tbb, strip, nstrips, lane); break;
+				case 1: aw_strip<false, 0, 1>(pr, K, tbb, strip, nstrips, lane); break;
+				case 2: aw_strip<false, 0, 2>(pr, K, tbb, strip, nstrips, lane); break;
+				case 3: aw_strip<false, 1, 0>(pr, K, tbb, strip, nstrips, lane); break;
+				case 4: aw_strip<false, 1, 1>(pr, K, tbb, strip, nstrips, lane); break;
+				case 5: aw_strip<false, 1, 2>(pr, K, tbb, strip, nstrips, lane); break;
+				case 6: aw_strip<false, 2, 0>(pr, K, tbb, strip, nstrips, lane); break;
+				case 7: aw_strip<false, 2, 1>(pr, K, tbb, strip, nstrips, lane); break;
+				default: aw_strip<false, 2, 2>(pr, K, tbb, strip, nstrips, lane); break;
 				}
-			const bool valid = i >= 1 && i <= LX && lane < nl;
-			const float p[AW_C] = { q.x, q.y, q.z, q.w };
-			if (lane < nl && i + 3 >= 1 && i + 3 <= LX)
-				q = *reinterpret_cast<const float4 *>(src + (size_t)(i + 2)*pr.ld);
-			if (valid)
-				{
-				float Y = recv;                                // new[i][first col - 1]
-				float diag = prevRecv;                         // new[i-1][first col - 1]
-				uint32_t word = 0;
-#pragma unroll
-				for (int c = 0; c < AW_C; ++c)
-					{
-					const float B = __fadd_rn(diag, p[c]);       // calcalnflat.cpp:31-37
-					const float X = old[c];
-					const float nw = fmaxf(fmaxf(B, X), Y);
-					const uint32_t code = (B >= X) ? ((B >= Y) ? 0u : 2u) : ((X >= Y) ? 1u : 2u);    // best3.h:5-28
-					word |= code << (2*c);
-					diag = X;
-					old[c] = nw;
-					Y = nw;
-					if (c == lastC && lane == lastLane && i == LX && lastStripHere)
-						*pr.score = nw;
-					}
-				outNew = Y;
-				tb[((size_t)(i - 1)*nstrips + strip)*32 + lane] = (uint8_t) word;
-				if (hasOut && lane == 31)
-					{
-					if (ringOut)
-						{
-						while (i > AW_RING && vcons[wid + 1] < i - AW_RING)
-							;                                     // the slot still holds an unconsumed row
-						ring_put(&ring[wid][i % AW_RING], outNew, i);
-						}
-					else
-						chan_put(chanOut + i, outNew, i);
-					}
-				}
-			prevRecv = recv;
-			__syncwarp();
-			};
-		int t = 0;
-		for (; t + 2 < nsteps; t += 3)
-			{
-			step(t, q0);
-			step(t + 1, q1);
-			step(t + 2, q2);
 			}
-		if (t < nsteps)
-			step(t, q0);
-		if (t + 1 < nsteps)
-			step(t + 1, q1);
 		}
 	__syncthreads();
 	// traceback (tracebackflat.cpp:3-37): TB(0,j) = 'Y', TB(i,0) = 'X'.  Done by warp 0 of the CTA that
 	// finishes last (the one owning the last strip), all lanes in lockstep on the same (i,j); the lanes
-	// hold the traceback bytes of 32 consecutive rows of the current 4-column group so that a dependent
-	// load is needed only every few steps.
+	// cache the traceback bytes of an 8-row x 4-group (16-column) tile whose corner is the current cell, so
+	// that a dependent load is needed about every 8 steps of a diagonal path.
 	const int npass = (nstrips + NW - 1)/NW;
 	if ((pass + 1)*NW < nstrips)
 		{
@@ -285,42 +379,40 @@ k_aln_wave(const AlnProblem *probs)
 		}
 	uint32_t n = 0;
 		{
-		const uint8_t *tbb = tb;
+		const uint8_t *tbb = TB_SMEM ? tb_sm : pr.tb;
+		const int rowpitch = nstrips*32;
 		int i = LX, j = LY;
 		int cbase = -1, cidx = -1;
 		uint32_t cw = 0;
-		while (i != 0 || j != 0)
+		const int lr = lane >> 2, lg = lane & 3;
+		while (i > 0 && j > 0)
 			{
-			char t;
-			if (i == 0)
-				t = 'Y';
-			else if (j == 0)
-				t = 'X';
-			else
+			const int jj = j - 1;
+			const int idx = jj >> 2;                         // column group (AW_C = 4; 32 groups per strip, numbered across strips)
+			const int dr = cbase - i, dg = cidx - idx;
+			if ((unsigned) dr >= 8u || (unsigned) dg >= 4u)
 				{
-				const int jj = j - 1;
-				const int idx = (jj/AW_W)*32 + (jj % AW_W)/AW_C;
-				int d = cbase - i;
-				if (idx != cidx || d < 0 || d >= 32)
-					{
-					cbase = i; cidx = idx; d = 0;
-					const int r = i - lane;
-					cw = 0u;
-					if (r >= 1)
-						cw = TB_SMEM ? (uint32_t) tbb[(size_t)(r - 1)*nstrips*32 + idx]
-						             : (uint32_t) __ldcv(tbb + (size_t)(r - 1)*nstrips*32 + idx);    // other CTAs wrote it
-					}
-				const uint32_t w = __shfl_sync(MB_FULL, cw, d);
-				const uint32_t code = (w >> (2*(jj % AW_C))) & 3u;
-				t = code == 0 ? 'B' : (code == 1 ? 'X' : 'Y');
+				cbase = i; cidx = idx;
+				const int r = i - lr, g = idx - lg;
+				cw = 0u;
+				if (r >= 1 && g >= 0)
+					cw = TB_SMEM ? (uint32_t) tbb[(size_t)(r - 1)*rowpitch + g]
+					             : (uint32_t) __ldcv(tbb + (size_t)(r - 1)*rowpitch + g);    // other CTAs wrote it
 				}
+			const uint32_t w = __shfl_sync(MB_FULL, cw, ((cbase - i) << 2) + (cidx - idx));
+			const uint32_t code = (w >> (2*(jj & 3))) & 3u;      // 0: B, 1: X, 2: Y
 			if (lane == 0)
-				pr.path[n] = t;
+				pr.path[n] = code == 0 ? 'B' : (code == 1 ? 'X' : 'Y');
 			++n;
-			if (t == 'B') { --i; --j; }
-			else if (t == 'X') --i;
-			else --j;
+			i -= (code != 2u);
+			j -= (code != 1u);
 			}
+		// first row / first column: only gaps are left
+		const char fill = i == 0 ? 'Y' : 'X';
+		const uint32_t rest = (uint32_t)(i + j);
+		for (uint32_t a = lane; a < rest; a += 32)
+			pr.path[n + a] = fill;
+		n += rest;
 		if (lane == 0)
 			{
 			pr.path[n] = 0;
@@ -793,6 +885,7 @@ __global__ void k_msa_update(const MsaJob J)
 // =============================================================================================
 // host side
 static inline size_t al256(size_t b) { return (b + 255)/256*256; }
+static inline size_t aw_dense_bytes(size_t LX, size_t ld) { return (LX + 1 + AW_PAD_BOT)*ld*sizeof(float); }
 
 struct JoinBufs                       // carved out of ctx->d_join
 	{
@@ -809,14 +902,14 @@ static int join_core(mb200_ctx *ctx, uint32_t na, uint32_t nb, const uint32_t *d
 	cudaStream_t st = ctx->stream;
 	const uint32_t ld = (cols_b + AW_C - 1)/AW_C*AW_C;
 	const uint32_t nstrips = (cols_b + AW_W - 1)/AW_W;
-	const size_t post_bytes = (size_t) cols_a*ld*sizeof(float);
+	const size_t post_bytes = aw_dense_bytes(cols_a, ld);         // incl. the zero row above and the padding below
 	const uint32_t nwarps = std::min<uint32_t>(AW_MAXW, nstrips);
 	const uint32_t npass = (nstrips + nwarps - 1)/nwarps;
 	const size_t tbw = (size_t) cols_a*nstrips*32;
 	const bool tb_smem = npass == 1 && tbw <= 192*1024;
 	const size_t chan_bytes = al256((size_t) npass*((size_t) cols_a + 1)*sizeof(uint2) + 256);
 	char *p = scratch;
-	B.post = (float *) p;            p += al256(post_bytes);
+	B.post = (float *) p + ld;       p += al256(post_bytes);
 	B.tb = (uint8_t *) p;            p += tb_smem ? 256 : al256(tbw);
 	B.edge = (uint2 *) p;            p += chan_bytes;
 	B.path = p;                      p += al256((size_t) cols_a + cols_b + 16);
@@ -826,7 +919,7 @@ static int join_core(mb200_ctx *ctx, uint32_t na, uint32_t nb, const uint32_t *d
 	B.ld = ld;
 	if ((size_t)(p - scratch) > scratch_bytes)
 		return mb_fail(ctx, MB200_EINVAL, "join scratch too small");
-	CU(cudaMemsetAsync(B.post, 0, post_bytes, st));
+	CU(cudaMemsetAsync(B.post - ld, 0, post_bytes, st));
 
 	BuildPostParams P;
 	P.n = ctx->nseq; P.na = na; P.nb = nb; P.cols_a = cols_a; P.cols_b = cols_b; P.ld = ld;
@@ -925,7 +1018,7 @@ static size_t join_scratch_bytes(uint32_t cols_a, uint32_t cols_b)
 	{
 	const uint32_t ld = (cols_b + AW_C - 1)/AW_C*AW_C;
 	const uint32_t nstrips = (cols_b + AW_W - 1)/AW_W;
-	return al256((size_t) cols_a*ld*4) + al256((size_t) cols_a*nstrips*32) + al256((size_t)(nstrips/AW_MAXW + 1)*((size_t) cols_a + 1)*8 + 256)
+	return al256(aw_dense_bytes(cols_a, ld)) + al256((size_t) cols_a*nstrips*32) + al256((size_t)(nstrips/AW_MAXW + 1)*((size_t) cols_a + 1)*8 + 256)
 	  + al256((size_t) cols_a + cols_b + 16) + 4*256;
 	}
 
@@ -974,7 +1067,7 @@ int mb200_align_pairs(mb200_ctx *ctx, uint32_t n, const uint32_t *store_pairs, c
 			return mb_fail(ctx, MB200_EINVAL, "path_off[%u..%u] leaves less than LX+LY+1 bytes", k, k + 1);
 		const uint32_t ld = (LY + AW_C - 1)/AW_C*AW_C;
 		const uint32_t nstrips = (LY + AW_W - 1)/AW_W;
-		dense_total += al256((uint64_t) LX*ld*4);
+		dense_total += al256(aw_dense_bytes(LX, ld));
 		tb_total += al256((uint64_t) LX*nstrips*32);
 		edge_total += al256((uint64_t)(nstrips/AW_MAXW + 1)*((uint64_t) LX + 1)*8 + 256);
 		lxmax = std::max(lxmax, LX);
@@ -1000,7 +1093,7 @@ int mb200_align_pairs(mb200_ctx *ctx, uint32_t n, const uint32_t *store_pairs, c
 		const uint32_t nstrips = (LY + AW_W - 1)/AW_W;
 		AlnProblem &q = probs[k];
 		q.LX = LX; q.LY = LY; q.ld = ld;
-		q.dense = (const float *)(d_dense + od);
+		q.dense = (const float *)(d_dense + od) + ld;
 		q.tb = (uint8_t *)(d_tb + ot);
 		q.edge = (uint2 *)(d_edge + oe);
 		q.done = (uint32_t *)(d_edge + oe + al256((uint64_t)(nstrips/AW_MAXW + 1)*((uint64_t) LX + 1)*8 + 256) - 256);
@@ -1010,9 +1103,9 @@ int mb200_align_pairs(mb200_ctx *ctx, uint32_t n, const uint32_t *store_pairs, c
 		DensifyJob &j = jobs[k];
 		j.rowoff = (const uint32_t *) ctx->d_rowoff.p + ctx->h_rowbase[sp];
 		j.entries = (const mb200_entry *) ctx->d_entries.p + ctx->h_entbase[sp];
-		j.dense = (float *)(d_dense + od);
+		j.dense = (float *)(d_dense + od) + ld;
 		j.LX = LX; j.ld = ld;
-		od += al256((uint64_t) LX*ld*4);
+		od += al256(aw_dense_bytes(LX, ld));
 		ot += al256((uint64_t) LX*nstrips*32);
 		oe += al256((uint64_t)(nstrips/AW_MAXW + 1)*((uint64_t) LX + 1)*8 + 256);
 		}
