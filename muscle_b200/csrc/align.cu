@@ -45,6 +45,7 @@
 static bool g_trace = false;
 static int g_trace_level = 0;          // 2: one line per join of >= 64 sequences
 static double g_t[6] = { 0, 0, 0, 0, 0, 0 };
+static double g_ts[5] = { 0, 0, 0, 0, 0 };   // sorted BuildPost path: count+order, emit, sort, runs, sum
 static unsigned g_calls = 0;
 static double now_s()
 	{
@@ -54,7 +55,11 @@ static void trace_report()
 	{
 	fprintf(stderr, "[mb200 trace] joins x%u: maps %.2f s, BuildPost gather %.2f s, apply %.2f s, decode DP %.2f s, "
 	  "map update %.2f s, host %.2f s\n", g_calls, g_t[0], g_t[1], g_t[2], g_t[3], g_t[4], g_t[5]);
+	if (g_ts[0] > 0)
+		fprintf(stderr, "[mb200 trace] BuildPost by cell: count+order %.2f s, emit %.2f s, sort %.2f s, runs %.2f s, sum %.2f s\n",
+		  g_ts[0], g_ts[1], g_ts[2], g_ts[3], g_ts[4]);
 	}
+#define TRACE_SUB(k) do { if (g_trace) { cudaStreamSynchronize(st); const double n_ = now_s(); g_ts[k] += n_ - tsub; tsub = n_; } } while (0)
 #define TRACE_MARK(k) do { if (g_trace) { cudaStreamSynchronize(st); const double n_ = now_s(); g_t[k] += n_ - tmark; tmark = n_; } } while (0)
 static void trace_init()
 	{
@@ -882,6 +887,247 @@ __global__ void k_msa_update(const MsaJob J)
 		p[i] = J.map[off + J.mark[off + p[i]]];
 	}
 
+// ---------------------------------------------------------------------------------------------
+// BuildPost for large joins: contributions bucketed by output cell.
+//
+// k_bp_apply keeps the reference's summation order by walking the (s,t) steps of an output row one
+// after the other: a conserved column is a chain of |A| x |B| dependent steps at ~400 cycles each
+// (one warp, ~30 instructions per step) -- 50 ms of a 72 ms refinement join at 1000 sequences.  The
+// order only matters PER CELL, so for large joins the contributions are written as (cell, value) pairs
+// in (s, residue, t) order -- which is (s,t) order for every cell, a sequence has one residue per
+// column -- bucketed by cell, and every run is summed front to back by one warp (coalesced loads, the
+// ordered adds by shuffle: ~5 cycles per term instead of ~400).  Bucketing costs two radix passes, not
+// four: the terms of a residue go to a position computed from a prefix sum over the residues ordered by
+// (row, s), so the stream is already in (row, s, t) order when it is written; a STABLE sort on the column
+// bits alone then leaves it in (col, row, s, t) order, i.e. every cell contiguous and in (s,t) order.
+struct BpCells
+	{
+	uint32_t s_lo, s_n;          // batch of sequences of A
+	const uint32_t *rb;          // [na+1] residues of A's members before member s
+	const uint32_t *rowof;       // [residues of A] column of A's alignment = row of post
+	const uint32_t *seqof;       // [residues of A] member of A that owns the residue
+	uint32_t *cnt;               // [(residue of the batch) x nb] terms of the pair's sparse row
+	uint64_t *eptr;              // [same] first entry of that sparse row: index into entries, bit 63 = transposed store
+	const uint32_t *off;         // exclusive scan of cnt (one more entry than cnt)
+	const uint32_t *base;        // [residue of the batch] first term of the residue in (row, s) order
+	uint32_t colbits;            // key = row << colbits | col
+	uint32_t *keys; float *vals; // [terms]
+	};
+
+__global__ void k_bp_rowof(const BuildPostParams P, const uint32_t *__restrict__ rb, uint32_t *__restrict__ rowof,
+  uint32_t *__restrict__ seqof)
+	{
+	const uint32_t s = blockIdx.y;
+	for (uint32_t c = blockIdx.x*blockDim.x + threadIdx.x; c < P.cols_a; c += gridDim.x*blockDim.x)
+		{
+		const int32_t pos = P.col2pos_a[(size_t) s*P.cols_a + c];
+		if (pos >= 0)
+			{
+			rowof[rb[s] + (uint32_t) pos] = c;
+			seqof[rb[s] + (uint32_t) pos] = s;
+			}
+		}
+	}
+
+// pass 1, one thread per (residue of the batch, member t of B): where the sparse row starts and how long it is
+__global__ void k_bpc_count(const BuildPostParams P, const BpCells G)
+	{
+	const uint32_t r0 = G.rb[G.s_lo];
+	const uint64_t total = (uint64_t)(G.rb[G.s_lo + G.s_n] - r0)*P.nb;
+	for (uint64_t idx = blockIdx.x*(uint64_t) blockDim.x + threadIdx.x; idx < total; idx += (uint64_t) gridDim.x*blockDim.x)
+		{
+		const uint32_t t = (uint32_t)(idx % P.nb);
+		const uint32_t r = r0 + (uint32_t)(idx/P.nb);
+		const uint32_t s = G.seqof[r];
+		const uint32_t pos = r - G.rb[s];
+		const uint32_t a = P.ids_a[s], b = P.ids_b[t];
+		uint32_t e0, e1;
+		uint64_t ep;
+		if (a < b)
+			{
+			const uint32_t q = (uint32_t)((uint64_t) a*P.n - (uint64_t) a*(a + 1)/2 + (b - a - 1));
+			const uint32_t *ro = P.rowoff + P.rowbase[q];
+			e0 = ro[pos]; e1 = ro[pos + 1];
+			ep = P.entbase[q] + e0;
+			}
+		else
+			{
+			const uint32_t q = (uint32_t)((uint64_t) b*P.n - (uint64_t) b*(b + 1)/2 + (a - b - 1));
+			const uint32_t *ro = P.troff + P.trbase[q];
+			e0 = ro[pos]; e1 = ro[pos + 1];
+			ep = (P.entbase[q] + e0) | (1ull << 63);
+			}
+		G.cnt[idx] = e1 - e0;
+		G.eptr[idx] = ep;
+		}
+	}
+
+// pass 2, eight lanes per (residue, t): the terms of the sparse row, one lane each
+__global__ void k_bpc_emit(const BuildPostParams P, const BpCells G)
+	{
+	const uint32_t r0 = G.rb[G.s_lo];
+	const uint64_t total = (uint64_t)(G.rb[G.s_lo + G.s_n] - r0)*P.nb;
+	const uint32_t sub = threadIdx.x & 7;
+	const uint64_t ngroups = ((uint64_t) gridDim.x*blockDim.x) >> 3;
+	for (uint64_t idx = (blockIdx.x*(uint64_t) blockDim.x + threadIdx.x) >> 3; idx < total; idx += ngroups)
+		{
+		const uint32_t n = G.cnt[idx];
+		if (n == 0)
+			continue;
+		const uint32_t t = (uint32_t)(idx % P.nb);
+		const uint32_t rl = (uint32_t)(idx/P.nb);
+		const uint64_t ep = G.eptr[idx];
+		const mb200_entry *en = ((ep >> 63) ? P.trentries : P.entries) + (ep & ~(1ull << 63));
+		const uint32_t *p2c = P.p2c_b + P.p2c_b_off[t];
+		const uint32_t kbase = G.rowof[r0 + rl] << G.colbits;
+		const uint32_t o = G.base[rl] + (G.off[idx] - G.off[(uint64_t) rl*P.nb]);
+		for (uint32_t k = sub; k < n; k += 8)
+			{
+			const mb200_entry v = en[k];
+			G.keys[o + k] = kbase | p2c[v.col];
+			G.vals[o + k] = v.p;                               // w1*w2*P with unit weights (buildpostflat.cpp:60-70)
+			}
+		}
+	}
+
+// residues of the batch -> (row, local index), to be ordered by row
+__global__ void k_bpc_reskeys(uint32_t nres, const uint32_t *__restrict__ rowof, uint32_t *__restrict__ keys, uint32_t *__restrict__ idx)
+	{
+	const uint32_t j = blockIdx.x*blockDim.x + threadIdx.x;
+	if (j < nres)
+		{ keys[j] = rowof[j]; idx[j] = j; }
+	}
+// terms of the residues in (row, s) order
+__global__ void k_bpc_resterms(uint32_t nres, uint32_t nb, const uint32_t *__restrict__ perm, const uint32_t *__restrict__ off,
+  uint32_t *__restrict__ nterms)
+	{
+	const uint32_t j = blockIdx.x*blockDim.x + threadIdx.x;
+	if (j < nres)
+		{
+		const uint64_t r = perm[j];
+		nterms[j] = off[(r + 1)*nb] - off[r*nb];
+		}
+	}
+__global__ void k_bpc_resbase(uint32_t nres, const uint32_t *__restrict__ perm, const uint32_t *__restrict__ start, uint32_t *__restrict__ base)
+	{
+	const uint32_t j = blockIdx.x*blockDim.x + threadIdx.x;
+	if (j < nres)
+		base[perm[j]] = start[j];
+	}
+
+// post[cell] += the terms of the cell's run, front to back.  The adds of one cell are a dependent chain
+// (4 cycles each); everything else must stay off that chain.  Runs are handed out longest first.
+//  * long runs (>= BPC_LONG terms): one warp per run streams the terms through a shared-memory double buffer
+//    with cp.async (the next BPC_CHUNK terms are in flight while lane 0 adds the current ones, four per
+//    LDS.128) -- ~5 cycles per term.  Measured alternatives on a 1000-sequence join: every lane adding
+//    shuffled terms 9 ms (one shuffle per cycle per SM, 600-cycle load exposed per 32 terms), one thread per
+//    run with 8 loads in flight 12 ms (the longest run, 41 600 terms, pays an L2 round trip per 8 terms).
+//  * short runs: one thread per run; the lanes of a warp get runs of about the same length.
+#define BPC_LONG 64
+#define BPC_CHUNK 512
+#define BPC_LWARPS 4
+__global__ void __launch_bounds__(32*BPC_LWARPS)
+k_bpc_sum_long(const uint32_t *__restrict__ perm, const uint32_t *__restrict__ ukeys, const uint32_t *__restrict__ ucnt,
+  const uint32_t *__restrict__ uoff, uint32_t nlong, const float *__restrict__ vals, float *__restrict__ post, uint32_t colbits, uint32_t ld)
+	{
+	__shared__ __align__(16) float buf[BPC_LWARPS][2][BPC_CHUNK];
+	const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+	const uint32_t j = blockIdx.x*BPC_LWARPS + wib;
+	if (j >= nlong)
+		return;
+	const uint32_t r = perm[j];
+	const uint32_t key = ukeys[r], n = ucnt[r];
+	const float *v = vals + uoff[r];
+	float *cell = post + (size_t)(key >> colbits)*ld + (key & ((1u << colbits) - 1u));
+	float acc = *cell;
+	const uint32_t nchunks = (n + BPC_CHUNK - 1)/BPC_CHUNK;
+	auto issue = [&](uint32_t c)
+		{
+		if (c < nchunks)
+			{
+			const uint32_t b0 = c*BPC_CHUNK;
+			float *dst = buf[wib][c & 1];
+#pragma unroll
+			for (uint32_t q = 0; q < BPC_CHUNK/32; ++q)
+				{
+				const uint32_t e = q*32 + lane;
+				if (b0 + e < n)
+					__pipeline_memcpy_async(dst + e, v + b0 + e, 4);
+				}
+			}
+		__pipeline_commit();
+		};
+	issue(0);
+	for (uint32_t c = 0; c < nchunks; ++c)
+		{
+		issue(c + 1);
+		__pipeline_wait_prior(1);
+		__syncwarp();
+		if (lane == 0)
+			{
+			const uint32_t m = min((uint32_t) BPC_CHUNK, n - c*BPC_CHUNK);
+			const float *src = buf[wib][c & 1];
+			uint32_t i = 0;
+			for (; i + 4 <= m; i += 4)
+				{
+				const float4 x = *reinterpret_cast<const float4 *>(src + i);
+				acc = __fadd_rn(acc, x.x); acc = __fadd_rn(acc, x.y); acc = __fadd_rn(acc, x.z); acc = __fadd_rn(acc, x.w);
+				}
+			for (; i < m; ++i)
+				acc = __fadd_rn(acc, src[i]);
+			}
+		__syncwarp();
+		}
+	if (lane == 0)
+		*cell = acc;
+	}
+
+__global__ void __launch_bounds__(128)
+k_bpc_sum_short(const uint32_t *__restrict__ perm, const uint32_t *__restrict__ ukeys, const uint32_t *__restrict__ ucnt,
+  const uint32_t *__restrict__ uoff, uint32_t first, uint32_t nruns, const float *__restrict__ vals, float *__restrict__ post,
+  uint32_t colbits, uint32_t ld)
+	{
+	const uint32_t j = first + blockIdx.x*blockDim.x + threadIdx.x;
+	if (j >= nruns)
+		return;
+	const uint32_t r = perm[j];
+	const uint32_t key = ukeys[r], n = ucnt[r];
+	const float *v = vals + uoff[r];
+	float *cell = post + (size_t)(key >> colbits)*ld + (key & ((1u << colbits) - 1u));
+	float acc = *cell;
+	uint32_t i = 0;
+	for (; i + 8 <= n; i += 8)
+		{
+		float x[8];
+#pragma unroll
+		for (int u = 0; u < 8; ++u)
+			x[u] = v[i + u];
+#pragma unroll
+		for (int u = 0; u < 8; ++u)
+			acc = __fadd_rn(acc, x[u]);
+		}
+	for (; i < n; ++i)
+		acc = __fadd_rn(acc, v[i]);
+	*cell = acc;
+	}
+// number of leading elements >= bound in a descending array
+__global__ void k_count_ge(const uint32_t *__restrict__ desc, uint32_t n, uint32_t bound, uint32_t *__restrict__ out)
+	{
+	uint32_t lo = 0, hi = n;                      // first index with desc[i] < bound
+	while (lo < hi)
+		{
+		const uint32_t mid = (lo + hi) >> 1;
+		if (desc[mid] >= bound) lo = mid + 1; else hi = mid;
+		}
+	*out = lo;
+	}
+__global__ void k_iota(uint32_t n, uint32_t *__restrict__ out)
+	{
+	const uint32_t j = blockIdx.x*blockDim.x + threadIdx.x;
+	if (j < n)
+		out[j] = j;
+	}
+
 // =============================================================================================
 // host side
 static inline size_t al256(size_t b) { return (b + 255)/256*256; }
@@ -930,6 +1176,160 @@ static int join_core(mb200_ctx *ctx, uint32_t na, uint32_t nb, const uint32_t *d
 	P.trentries = (const mb200_entry *) ctx->d_tr_entries.p;
 	P.entbase = (const uint64_t *) ctx->d_entbase.p;
 	P.post = B.post;
+	// large joins: bucket the contributions by cell (see k_bpc_*); small ones: ordered row walk (k_bp_apply)
+	size_t nbatches = 0;
+	const char *ev_sort = getenv("MB200_BP_SORT_MIN");             // tuning hook: (residues of A) x |B| from which to sort
+	const long long sort_min = ev_sort ? atoll(ev_sort) : 1000000ll;
+	uint32_t colbits = 1, rowbits = 1;
+	while ((1u << colbits) < cols_b)
+		++colbits;
+	while ((1u << rowbits) < cols_a)
+		++rowbits;
+	if ((uint64_t) h_rb[na]*nb >= (uint64_t) sort_min && colbits + rowbits <= 32 && na <= 65535)
+		{
+		// batches of sequences of A: at most ~16M (residue, t) rows each
+		const uint64_t budget_rt = 16ull << 20;
+		std::vector<uint32_t> cuts(1, 0);
+		uint64_t max_rt = 0;
+		uint32_t max_res = 0;
+		for (uint32_t s0 = 0; s0 < na; )
+			{
+			uint32_t e = s0 + 1;
+			while (e < na && (uint64_t)(h_rb[e + 1] - h_rb[s0])*nb <= budget_rt)
+				++e;
+			max_rt = std::max<uint64_t>(max_rt, (uint64_t)(h_rb[e] - h_rb[s0])*nb);
+			max_res = std::max(max_res, h_rb[e] - h_rb[s0]);
+			cuts.push_back(e);
+			s0 = e;
+			}
+		if (max_rt >= 0x7ffffff0ull)
+			return mb_fail(ctx, MB200_EOVERFLOW, "BuildPost batch of %llu rows", (unsigned long long) max_rt);
+		// d_tmp: rowof, seqof [residues] | cnt [max_rt+1] | off [max_rt+1] | eptr [max_rt] | 5 x [max_res] | nruns | cub scratch
+		const size_t rowof_b = al256((size_t) h_rb[na]*4), rt_b = al256((size_t)(max_rt + 1)*4), res_b = al256((size_t) max_res*4);
+		size_t scan_tb = 0, rsort_tb = 0;
+		cub::DeviceScan::ExclusiveSum(nullptr, scan_tb, (const uint32_t *) nullptr, (uint32_t *) nullptr, (int)(max_rt + 1), st);
+		cub::DeviceRadixSort::SortPairs(nullptr, rsort_tb, (const uint32_t *) nullptr, (uint32_t *) nullptr,
+		  (const uint32_t *) nullptr, (uint32_t *) nullptr, (int) max_res, 0, (int) rowbits, st);
+		const size_t tb1 = al256(std::max(scan_tb, rsort_tb));
+		ENSURE(ctx->d_tmp, 2*rowof_b + 4*rt_b + 5*res_b + 256 + tb1);
+		char *tp = (char *) ctx->d_tmp.p;
+		uint32_t *d_rowof = (uint32_t *) tp;             tp += rowof_b;
+		uint32_t *d_seqof = (uint32_t *) tp;             tp += rowof_b;
+		uint64_t *d_eptr = (uint64_t *) tp;              tp += 2*rt_b;
+		uint32_t *d_cnt = (uint32_t *) tp;               tp += rt_b;
+		uint32_t *d_off = (uint32_t *) tp;               tp += rt_b;
+		uint32_t *d_rk = (uint32_t *) tp;                tp += res_b;      // row of the residue / sorted
+		uint32_t *d_ri = (uint32_t *) tp;                tp += res_b;      // local index
+		uint32_t *d_rk2 = (uint32_t *) tp;               tp += res_b;
+		uint32_t *d_perm = (uint32_t *) tp;              tp += res_b;      // residues in (row, s) order
+		uint32_t *d_base = (uint32_t *) tp;              tp += res_b;
+		uint32_t *d_nruns = (uint32_t *) tp;             tp += 256;
+		void *d_scratch1 = tp;
+		k_bp_rowof<<<dim3((cols_a + 255)/256, na), 256, 0, st>>>(P, d_rb, d_rowof, d_seqof);
+		CU(cudaGetLastError());
+		const int sms = ctx->prop.multiProcessorCount;
+		nbatches = cuts.size() - 1;
+		for (size_t b = 0; b + 1 < cuts.size(); ++b)
+			{
+			double tsub = now_s();
+			BpCells C;
+			C.s_lo = cuts[b]; C.s_n = cuts[b + 1] - cuts[b];
+			C.rb = d_rb; C.rowof = d_rowof; C.seqof = d_seqof; C.cnt = d_cnt; C.eptr = d_eptr; C.off = d_off; C.base = d_base;
+			C.colbits = colbits;
+			C.keys = nullptr; C.vals = nullptr;
+			const uint32_t nres = h_rb[cuts[b + 1]] - h_rb[cuts[b]];
+			const uint64_t rt = (uint64_t) nres*nb;
+			const uint32_t gblocks = (uint32_t) std::min<uint64_t>((rt + 255)/256, (uint64_t) sms*32);
+			const uint32_t rblocks = (nres + 255)/256;
+			k_bpc_count<<<gblocks, 256, 0, st>>>(P, C);
+			CU(cudaMemsetAsync(d_cnt + rt, 0, 4, st));
+			size_t t0 = tb1;
+			cub::DeviceScan::ExclusiveSum(d_scratch1, t0, (const uint32_t *) d_cnt, d_off, (int)(rt + 1), st);
+			CU(cudaGetLastError());
+			CU(cudaMemcpyAsync(ctx->h_pinned + 4, d_off + rt, 4, cudaMemcpyDeviceToHost, st));
+			// residues ordered by (row, s): the input order is s-major, the sort is stable
+			k_bpc_reskeys<<<rblocks, 256, 0, st>>>(nres, d_rowof + h_rb[cuts[b]], d_rk, d_ri);
+			t0 = tb1;
+			cub::DeviceRadixSort::SortPairs(d_scratch1, t0, (const uint32_t *) d_rk, d_rk2, (const uint32_t *) d_ri, d_perm,
+			  (int) nres, 0, (int) rowbits, st);
+			k_bpc_resterms<<<rblocks, 256, 0, st>>>(nres, nb, d_perm, d_off, d_rk);           // d_rk: terms per residue, sorted order
+			t0 = tb1;
+			cub::DeviceScan::ExclusiveSum(d_scratch1, t0, (const uint32_t *) d_rk, d_rk2, (int) nres, st);
+			k_bpc_resbase<<<rblocks, 256, 0, st>>>(nres, d_perm, d_rk2, d_base);
+			CU(cudaGetLastError());
+			CU(cudaStreamSynchronize(st));
+			const uint64_t M = ctx->h_pinned[4];
+			if (M >= 0x7fffffffull)
+				return mb_fail(ctx, MB200_EOVERFLOW, "BuildPost batch of %llu terms", (unsigned long long) M);
+			if (M == 0)
+				continue;
+			// d_stage: keys_in | vals_in | keys_out | vals_out | run offsets | cub scratch
+			const size_t mb = al256((size_t) M*4);
+			size_t sort_tb = 0, rle_tb = 0, scan2_tb = 0;
+			cub::DeviceRadixSort::SortPairs(nullptr, sort_tb, (const uint32_t *) nullptr, (uint32_t *) nullptr,
+			  (const float *) nullptr, (float *) nullptr, (int) M, 0, (int) colbits, st);
+			cub::DeviceRunLengthEncode::Encode(nullptr, rle_tb, (const uint32_t *) nullptr, (uint32_t *) nullptr, (uint32_t *) nullptr,
+			  (uint32_t *) nullptr, (int) M, st);
+			cub::DeviceScan::ExclusiveSum(nullptr, scan2_tb, (const uint32_t *) nullptr, (uint32_t *) nullptr, (int) M, st);
+			const size_t tb = std::max(sort_tb, std::max(rle_tb, scan2_tb));
+			ENSURE(ctx->d_stage, 5*mb + al256(tb) + 256);
+			char *sp = (char *) ctx->d_stage.p;
+			uint32_t *keys_in = (uint32_t *) sp;              float *vals_in = (float *)(sp + mb);
+			uint32_t *keys_out = (uint32_t *)(sp + 2*mb);     float *vals_out = (float *)(sp + 3*mb);
+			uint32_t *uoff = (uint32_t *)(sp + 4*mb);
+			void *scratch2 = sp + 5*mb;
+			C.keys = keys_in; C.vals = vals_in;
+			TRACE_SUB(0);
+			k_bpc_emit<<<(uint32_t) std::min<uint64_t>((rt*8 + 255)/256, (uint64_t) sms*32), 256, 0, st>>>(P, C);
+			CU(cudaGetLastError());
+			TRACE_SUB(1);
+			TRACE_MARK(1);
+			// stable sort on the column bits only: (row, s, t) order survives inside every column
+			size_t t1 = sort_tb;
+			cub::DeviceRadixSort::SortPairs(scratch2, t1, (const uint32_t *) keys_in, keys_out, (const float *) vals_in, vals_out,
+			  (int) M, 0, (int) colbits, st);
+			TRACE_SUB(2);
+			// runs of equal cells: unique keys and lengths reuse the input buffers
+			uint32_t *ukeys = keys_in, *ucnt = (uint32_t *) vals_in;
+			size_t t2 = rle_tb;
+			cub::DeviceRunLengthEncode::Encode(scratch2, t2, (const uint32_t *) keys_out, ukeys, ucnt, d_nruns, (int) M, st);
+			CU(cudaGetLastError());
+			CU(cudaMemcpyAsync(ctx->h_pinned + 4, d_nruns, 4, cudaMemcpyDeviceToHost, st));
+			CU(cudaStreamSynchronize(st));
+			const uint32_t nruns = ctx->h_pinned[4];
+			size_t t3 = scan2_tb;
+			cub::DeviceScan::ExclusiveSum(scratch2, t3, (const uint32_t *) ucnt, uoff, (int) nruns, st);
+			// runs by descending length (d_tmp2: counts out | index in | index out | cub scratch)
+			size_t lsort_tb = 0;
+			cub::DeviceRadixSort::SortPairsDescending(nullptr, lsort_tb, (const uint32_t *) nullptr, (uint32_t *) nullptr,
+			  (const uint32_t *) nullptr, (uint32_t *) nullptr, (int) nruns, 0, 32, st);
+			const size_t nrb = al256((size_t) nruns*4);
+			ENSURE(ctx->d_tmp2, 3*nrb + al256(lsort_tb));
+			uint32_t *d_lc = (uint32_t *) ctx->d_tmp2.p;
+			uint32_t *d_li = (uint32_t *)((char *) ctx->d_tmp2.p + nrb);
+			uint32_t *d_lperm = (uint32_t *)((char *) ctx->d_tmp2.p + 2*nrb);
+			void *d_lscratch = (char *) ctx->d_tmp2.p + 3*nrb;
+			k_iota<<<(nruns + 255)/256, 256, 0, st>>>(nruns, d_li);
+			cub::DeviceRadixSort::SortPairsDescending(d_lscratch, lsort_tb, (const uint32_t *) ucnt, d_lc, (const uint32_t *) d_li, d_lperm,
+			  (int) nruns, 0, 32, st);
+			k_count_ge<<<1, 1, 0, st>>>(d_lc, nruns, BPC_LONG, d_nruns + 1);
+			CU(cudaMemcpyAsync(ctx->h_pinned + 5, d_nruns + 1, 4, cudaMemcpyDeviceToHost, st));
+			CU(cudaStreamSynchronize(st));
+			const uint32_t nlong = ctx->h_pinned[5];
+			TRACE_SUB(3);
+			if (nlong > 0)
+				k_bpc_sum_long<<<(nlong + BPC_LWARPS - 1)/BPC_LWARPS, 32*BPC_LWARPS, 0, st>>>(d_lperm, ukeys, ucnt, uoff, nlong, vals_out,
+				  B.post, colbits, ld);
+			if (nruns > nlong)
+				k_bpc_sum_short<<<(nruns - nlong + 127)/128, 128, 0, st>>>(d_lperm, ukeys, ucnt, uoff, nlong, nruns, vals_out, B.post, colbits, ld);
+			CU(cudaGetLastError());
+			TRACE_SUB(4);
+			TRACE_MARK(2);
+			ctx->stats.kernel_launches += 14;
+			}
+		}
+	else
+		{
 	// the accumulator rows of BP_WARPS warps + their cp.async double buffers must fit in shared memory
 	const size_t acc_smem = (((size_t) BP_WARPS*cols_b*sizeof(float) + 15) & ~(size_t) 15) + (size_t) BP_WARPS*BP_NBUF*BP_G*BP_W*sizeof(uint2);
 	if (acc_smem > 220*1024)
@@ -949,6 +1349,7 @@ static int join_core(mb200_ctx *ctx, uint32_t na, uint32_t nb, const uint32_t *d
 		s = e;
 		}
 	ENSURE(ctx->d_stage, max_slots*BP_W*sizeof(uint2) + 256);
+	nbatches = cuts.size() - 1;
 	BpStage G;
 	G.slots = (uint2 *) ctx->d_stage.p;
 	G.rb = d_rb;
@@ -990,6 +1391,7 @@ static int join_core(mb200_ctx *ctx, uint32_t na, uint32_t nb, const uint32_t *d
 		}
 	ctx->stats.kernel_launches += 2;
 	CU(cudaGetLastError());
+		}
 	AlnProblem pr;
 	pr.LX = cols_a; pr.LY = cols_b; pr.ld = ld; pr.dense = B.post; pr.tb = B.tb; pr.edge = B.edge;
 	pr.done = (uint32_t *)((char *) B.edge + chan_bytes - 256);
@@ -1010,7 +1412,7 @@ static int join_core(mb200_ctx *ctx, uint32_t na, uint32_t nb, const uint32_t *d
 	TRACE_MARK(3);
 	if (g_trace_level >= 2 && na + nb >= 64)
 		fprintf(stderr, "[mb200 join] %u x %u seqs, %u x %u cols, %zu batch(es): DP %.2f ms (BuildPost totals so far: gather %.1f ms apply %.1f ms)\n",
-		  na, nb, cols_a, cols_b, cuts.size() - 1, 1e3*(g_t[3] - g3), 1e3*g1, 1e3*g2);
+		  na, nb, cols_a, cols_b, nbatches, 1e3*(g_t[3] - g3), 1e3*g1, 1e3*g2);
 	return MB200_OK;
 	}
 

@@ -106,7 +106,9 @@ def test_align_pairs_vs_oracle(engine, oracle):
 		assert np.float32(s) == scores[k] and path == paths[k], k
 
 
-def test_align_groups_vs_oracle(engine, oracle):
+@pytest.mark.parametrize("bp_sort_min", ["1000000000000", "0"])      # ordered row walk / contributions sorted by cell
+def test_align_groups_vs_oracle(engine, oracle, monkeypatch, bp_sort_min):
+	monkeypatch.setenv("MB200_BP_SORT_MIN", bp_sort_min)
 	seqs = synth.make_family(7, 70, 10, seed=21)
 	lens = [len(s) for s in seqs]
 	engine.set_seqs(seqs)

@@ -43,8 +43,10 @@ def rows_from_device(engine, seqs, ids):
 	return out
 
 
+@pytest.mark.parametrize("bp_sort_min", ["1000000000000", "0"])      # both BuildPost paths of the library
 @pytest.mark.parametrize("n,L,seed", [(9, 70, 7), (14, 110, 8)])
-def test_progressive_and_refinement_on_device(engine, n, L, seed):
+def test_progressive_and_refinement_on_device(engine, n, L, seed, monkeypatch, bp_sort_min):
+	monkeypatch.setenv("MB200_BP_SORT_MIN", bp_sort_min)
 	seqs = synth.make_family(n, L, L//4, seed=seed)
 	engine.set_seqs(seqs)
 	engine.posteriors_allpairs()
