@@ -24,8 +24,9 @@
 // one term per (s,t); the order is kept per cell, everything else is parallel.  Phase 1 (k_bp_gather,
 // one thread per (residue of A's members, t)) does the random gathers into the store and writes each
 // needed sparse row, mapped to columns of B, into a 16-entry staging slot; phase 2 (k_bp_apply, one warp per row,
-// accumulator row in shared memory) streams the slots through a cp.async double buffer and applies
-// them strictly in order, the entries of one sparse row in parallel.
+// accumulator row in shared memory) streams the slots through a cp.async ring and applies
+// them strictly in order, the entries of one sparse row in parallel.  Large joins take another route
+// (k_bpc_*, further down): the terms are bucketed by output cell and every cell is summed front to back.
 #include "engine.h"
 #include <cuda_pipeline.h>
 #include <cub/cub.cuh>

@@ -2,8 +2,9 @@
 engine (integration/_build/muscle_b200, built from integration/mpcflat_b200_shim.cpp) against the
 MSAs the unmodified CPU reference produced for the same FASTA (tests/golden/e2e/*.ref.afa).
 
-Bar (SURVEY.md section 7 hard part 2): identical MSA; where an expf-ulp flip at the 0.01 cut makes
-rows differ, at least 98 % of aligned residue pairs must agree."""
+Bar: the identical MSA, row for row.  Every stage of the device path is bit-exact (including expf at the
+0.01 cut), so there is no tolerance on aligned pairs any more; on a mismatch the fraction of shared
+aligned residue pairs is reported to help debugging."""
 import os
 import subprocess
 import pytest
@@ -60,7 +61,7 @@ def test_align_cli_matches_reference_msa(name, tmp_path):
 		return
 	a, b = pair_set(got), pair_set(want)
 	q = len(a & b)/max(1, len(b))
-	assert q >= 0.98, "MSA differs from the reference: shared aligned pairs %.4f" % q
+	assert False, "MSA differs from the reference: shared aligned pairs %.4f" % q
 
 
 def test_super5_cli_matches_reference_msa(tmp_path):
@@ -84,7 +85,7 @@ def test_super5_cli_matches_reference_msa(tmp_path):
 		return
 	a, b = pair_set(got), pair_set(want)
 	q = len(a & b)/max(1, len(b))
-	assert q >= 0.98, "super5 MSA differs from the reference: shared aligned pairs %.4f" % q
+	assert False, "super5 MSA differs from the reference: shared aligned pairs %.4f" % q
 
 
 def test_profalign_cli_matches_reference_msa(tmp_path):
