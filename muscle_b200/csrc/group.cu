@@ -120,21 +120,26 @@ int mb200_group_create(int ndev, const int *devices, mb200_group **out)
 	g->ndev = (int) g->ctx.size();
 	// peer access between every pair of devices (NVLink / NVSwitch); without it the copies below
 	// would be staged through the host
-	for (int a = 0; a < g->ndev; ++a)
-		for (int b = 0; b < g->ndev; ++b)
-			{
-			if (a == b)
-				continue;
-			int can = 0;
-			cudaDeviceCanAccessPeer(&can, devs[a], devs[b]);
-			if (can)
+	// (one thread per source device: enabling a peer mapping takes ~0.1 s and there are ndev*(ndev-1) of them)
+		{
+		std::vector<std::thread> th;
+		for (int a = 0; a < g->ndev; ++a)
+			th.emplace_back([&, a]
 				{
 				cudaSetDevice(devs[a]);
-				const cudaError_t e = cudaDeviceEnablePeerAccess(devs[b], 0);
-				if (e != cudaSuccess)
-					cudaGetLastError();          // already enabled is fine
-				}
-			}
+				for (int b = 0; b < g->ndev; ++b)
+					{
+					if (a == b)
+						continue;
+					int can = 0;
+					cudaDeviceCanAccessPeer(&can, devs[a], devs[b]);
+					if (can && cudaDeviceEnablePeerAccess(devs[b], 0) != cudaSuccess)
+						cudaGetLastError();          // already enabled is fine
+					}
+				});
+		for (auto &t : th)
+			t.join();
+		}
 	g->lo.assign(g->ndev, 0);
 	g->hi.assign(g->ndev, 0);
 	*out = g;
@@ -272,12 +277,11 @@ int mb200_group_posteriors_allpairs(mb200_group *g, float *ea_out)
 		}
 	std::vector<uint32_t *> dst_off(g->ndev, nullptr);
 	std::vector<mb200_entry *> dst_ent(g->ndev, nullptr);
-	for (int d = 0; d < g->ndev; ++d)
-		{
-		rc = mb200_store_exchange_begin(g->ctx[d], g->off_pos[g->ndev], g->ent_pos[g->ndev], &dst_off[d], &dst_ent[d]);
-		if (rc != MB200_OK)
-			return gfail(g, rc, "device %d: %s", g->ctx[d]->device, mb200_last_error(g->ctx[d]));
-		}
+	// (in parallel: every device allocates buffers for the whole store here)
+	rc = on_all(g, [&](int d)
+		{ return mb200_store_exchange_begin(g->ctx[d], g->off_pos[g->ndev], g->ent_pos[g->ndev], &dst_off[d], &dst_ent[d]); });
+	if (rc != MB200_OK)
+		return rc;
 	// one stream per SOURCE device carries its image to every destination (itself included)
 	for (int r = 0; r < g->ndev; ++r)
 		{
