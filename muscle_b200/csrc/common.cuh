@@ -43,9 +43,10 @@ __constant__ float4 c_logexp1[4] =
 //  * the LOGEXP1 piece (cut points 1, 2.5, 4.5: all multiples of 1/2, intervals closed on the right)
 //    is found WITHOUT compares: k = ceil(2d) is formed in the mantissa of 2d + 1.5*2^23 by one
 //    FFMA with round-up, and k*16 added to a pre-biased base is the shared-memory address of a
-//    16-entry {c3,c2,c1,c0} table (k = 0..2 -> piece 0, 3..5 -> 1, 6..9 -> 2, 10..15 -> 3).  The load
-//    is predicated on d < 7.5 (for larger gaps the address is meaningless and the polynomial result is
-//    discarded by the final select).  Round 1 spent 8 of its 17 instructions per LOG_ADD on the
+//    17-entry {c3,c2,c1,c0} table (k = 0..2 -> piece 0, 3..5 -> 1, 6..9 -> 2, 10..16 -> 3).  The gap is
+//    clamped to 7.75 before the index is formed, so the load is always inside the table; for d >= 7.5 the
+//    polynomial result is discarded by the final select.  (A predicated-load version in inline PTX spilled
+//    272 bytes at 96 registers and was slower: profiles/r02_SUMMARY.md.)  Round 1 spent 8 of its 17 instructions per LOG_ADD on the
 //    half-rate ALU pipe (two compare/select pairs for the piece, min, max, gap test, select); this
 //    form is 14 instructions with 4 on the ALU pipe (profiles/r01_SUMMARY.md: ALU pipe 58 % busy).
 //  The arithmetic (sub, three mul/add Horner steps with separate roundings, final add) is written
@@ -59,26 +60,6 @@ struct LogAdd
 		const float d = fabsf(__fsub_rn(x, y));
 		const float lo = fminf(x, y);
 		const float hi = fmaxf(x, y);
-#ifdef MB_LA_ASM
-		const float t = __fmaf_ru(d, 2.0f, 12582912.0f);
-		const uint32_t addr = tab + (__float_as_uint(t) << 4);
-		float r;
-		asm("{\n\t"
-		    ".reg .pred p;\n\t"
-		    ".reg .f32 c3, c2, c1, c0, q;\n\t"
-		    "setp.lt.f32 p, %1, 0f40F00000;\n\t"                      // d < 7.5
-		    "@p ld.shared.v4.f32 {c3, c2, c1, c0}, [%2];\n\t"
-		    "mul.rn.f32 q, c3, %1;\n\t"
-		    "add.rn.f32 q, q, c2;\n\t"
-		    "mul.rn.f32 q, q, %1;\n\t"
-		    "add.rn.f32 q, q, c1;\n\t"
-		    "mul.rn.f32 q, q, %1;\n\t"
-		    "add.rn.f32 q, q, c0;\n\t"
-		    "add.rn.f32 q, q, %3;\n\t"
-		    "selp.f32 %0, q, %4, p;\n\t"
-		    "}"
-		    : "=f"(r) : "f"(d), "r"(addr), "f"(lo), "f"(hi));
-#else
 		// the address stays inside the 17-entry table for any gap (entry 16 is never used for a result)
 		const float t = __fmaf_ru(fminf(d, 7.75f), 2.0f, 12582912.0f);
 		const uint32_t addr = tab + (__float_as_uint(t) << 4);
@@ -88,13 +69,11 @@ struct LogAdd
 		q = ADD(MUL(q, d), c.z);
 		q = ADD(MUL(q, d), c.w);
 		const float r = d >= 7.5f ? hi : ADD(q, lo);
-#endif
 		return r;
 		}
 	};
 
-// builds the 16-entry table in shared memory (call with >= 16 threads, then __syncthreads) and
-// returns the functor
+// builds the 17-entry table in shared memory (call with >= 17 threads, then __syncthreads)
 __device__ __forceinline__ void mb_logadd_fill(float4 *tab16)
 	{
 	if (threadIdx.x < 17)
