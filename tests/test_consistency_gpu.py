@@ -136,6 +136,31 @@ def test_align_groups_vs_oracle(engine, oracle, monkeypatch, bp_sort_min):
 	assert np.float32(s2) == np.float32(score2) and pth2 == path2
 
 
+def test_align_groups_large_join_paths_agree(engine, monkeypatch):
+	"""A join above the library's own threshold (>= 1e6 (residue, member) rows) takes the bucketed-by-cell
+	BuildPost on its own; the column-posterior matrix, the path and the score must equal the ordered row walk
+	bit for bit (two staggered ungapped groups of 64 sequences)."""
+	seqs = synth.make_family(128, 260, 40, seed=77)
+	engine.set_seqs(seqs)
+	engine.posteriors_allpairs()
+	rng = np.random.default_rng(5)
+	ids1, ids2 = list(range(0, 128, 2)), list(range(1, 128, 2))
+	sh1 = {i: int(rng.integers(0, 12)) for i in ids1}
+	sh2 = {i: int(rng.integers(0, 12)) for i in ids2}
+	c1 = max(len(seqs[i]) + sh1[i] for i in ids1)
+	c2 = max(len(seqs[i]) + sh2[i] for i in ids2)
+	p1 = [np.arange(len(seqs[i]), dtype=np.uint32) + sh1[i] for i in ids1]
+	p2 = [np.arange(len(seqs[i]), dtype=np.uint32) + sh2[i] for i in ids2]
+	assert sum(len(seqs[i]) for i in ids1)*len(ids2) >= 1000000
+	monkeypatch.setenv("MB200_BP_SORT_MIN", "1000000000000")
+	s_walk, path_walk, post_walk = engine.align_groups(ids1, p1, c1, ids2, p2, c2, want_post=True)
+	monkeypatch.delenv("MB200_BP_SORT_MIN")
+	s_sort, path_sort, post_sort = engine.align_groups(ids1, p1, c1, ids2, p2, c2, want_post=True)
+	assert post_sort.tobytes() == post_walk.tobytes()
+	assert path_sort == path_walk and np.float32(s_sort) == np.float32(s_walk)
+	assert float(post_sort.max()) > 1.0          # conserved columns: long ordered sums
+
+
 @pytest.mark.parametrize("world", [3, 8])
 def test_virtual_ranks_pipeline(tables, oracle, world):
 	"""the sharded pipeline with `world` virtual ranks on one GPU (no NCCL): every rank computes its
