@@ -34,6 +34,7 @@ static vector<uint> g_MSAOrder;                    // input-sequence index of ev
 // MB200_TRACE=1: wall-time split of the replaced members, printed at exit
 static double g_TPost = 0, g_TCons = 0, g_TProg = 0, g_TRefine = 0, g_TAlign = 0;
 static uint g_NAlign = 0, g_NJoin = 0;
+static double g_TCreate = 0, g_TUpload = 0, g_TPostCall = 0;      // parts of CalcPosteriors
 static double Now()
 	{
 	return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
@@ -48,6 +49,8 @@ static void TraceReport()
 	  "(last: kernel %.1f ms, exchange %.1f ms), ProgressiveAlign %.2f s, Refine %.2f s (%u device joins), AlignAlns x%u %.2f s\n",
 	  S.ndev, g_TPost, S.exchange1_ms, S.exchange1_bytes_per_dev/1e9, g_TCons, S.relax_kernel_ms, S.exchange2_ms,
 	  g_TProg, g_TRefine, g_NJoin, g_NAlign, g_TAlign);
+	fprintf(stderr, "[mb200 trace] CalcPosteriors: contexts %.2f s, tables+sequences %.2f s, posteriors call %.2f s (kernels %.0f ms)\n",
+	  g_TCreate, g_TUpload, g_TPostCall, S.posterior_ms);
 	}
 
 static void Check(int rc, const char *What)
@@ -87,7 +90,9 @@ static void EnsureGroup()
 // the whole posterior stage of one MPCFlat object on the device(s)
 static void RunPosteriors(MPCFlat &M)
 	{
+	double TS = Now();
 	EnsureGroup();
+	g_TCreate += Now() - TS; TS = Now();
 	const uint SeqCount = M.GetSeqCount();
 	const uint PairCount = SIZE(M.m_Pairs);
 	asserta(PairCount > 0);
@@ -150,8 +155,10 @@ static void RunPosteriors(MPCFlat &M)
 		CheckG(mb200_group_set_seqs(g_Group, SeqCount, Bytes.data(), Offsets.data()), "mb200_group_set_seqs");
 		}
 
+	g_TUpload += Now() - TS; TS = Now();
 	vector<float> EAs(PairCount);
 	CheckG(mb200_group_posteriors_allpairs(g_Group, EAs.data()), "mb200_group_posteriors_allpairs");
+	g_TPostCall += Now() - TS;
 	for (uint PairIndex = 0; PairIndex < PairCount; ++PairIndex)
 		{
 		const pair<uint, uint> &Pair = M.GetPair(PairIndex);
